@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Benchmark of the `inference` hot path (BASELINE.json metric: Mvoxels/s for the 3-channel
+affinity U-Net on a 1024^3 uint8 chunk at 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...           # the reference algorithm on the host CPUs
+
+A "step" is one pass of the hot path over one synthetic chunk per GPU (weak scaling: one
+independent chunk per rank, no data-path collective).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MODEL_FILE = os.path.join(ROOT, "chunkflow_b200", "convnet", "unet3l.py")
+
+WORKLOADS = {
+    # name: (chunk zyx, patch, overlap)   -- BASELINE.json configs #3/#4 and #2
+    "1024": ((1024, 1024, 1024), (32, 256, 256), (8, 64, 64)),
+    "512": ((512, 512, 512), (20, 256, 256), (4, 64, 64)),
+    "256": ((256, 512, 512), (32, 256, 256), (8, 64, 64)),   # quick functional check, not a bench line
+}
+FLOP_PER_PATCH_VOXEL = 141248
+CONV3_FLOP = {  # per full-resolution patch voxel, 3x3x3 layers only (by kernel class name)
+    "enc0.0": 864, "enc0.2": 13824, "enc1.0": 27648 / 4, "enc1.2": 55296 / 4, "enc2.0": 110592 / 16,
+    "enc2.2": 221184 / 16, "dec1.0": 110592 / 4, "dec1.2": 55296 / 4, "dec0.0": 27648, "dec0.2": 13824,
+}
+
+
+def patch_count(chunk, patch, overlap):
+    n = 1
+    for c, p, o in zip(chunk, patch, overlap):
+        n *= len(range(0, c - o, p - o))
+    return n
+
+
+def synthetic_chunk(shape, seed, pinned=True):
+    """uint8 chunk from np.random.default_rng(20260922 + k)."""
+    import torch
+    rng = np.random.default_rng(seed)
+    if pinned and torch.cuda.is_available():
+        t = torch.empty(shape, dtype=torch.uint8, pin_memory=True)
+        a = t.numpy()
+    else:
+        t, a = None, np.empty(shape, np.uint8)
+    for z in range(0, shape[0], 64):  # slab-wise to bound temporary memory
+        a[z:z + 64] = rng.integers(0, 256, size=a[z:z + 64].shape, dtype=np.uint8)
+    return t, a
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm, smax, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); smax = max(smax, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_sample(chunk_shape, patch, overlap, n_patches, seed, threads):
+    """Times the reference algorithm (oracle port: torch-CPU network + numpy extract/blend) on the
+    first `n_patches` patches of the workload; returns seconds per patch incl. extract and blend."""
+    import torch
+    from chunkflow_b200.lib import load_source
+    from oracle import inferencer_oracle as O
+    torch.set_num_threads(threads)
+    model = load_source(MODEL_FILE).load_model(None)
+    # a sub-chunk that holds n_patches whole patches of the real geometry (same patch size / overlap)
+    nx = min(n_patches, 2)
+    nz = (n_patches + nx - 1) // nx
+    sub = (patch[0] + (nz - 1) * (patch[0] - overlap[0]), patch[1], patch[2] + (nx - 1) * (patch[2] - overlap[2]))
+    sub = tuple(min(s, c) for s, c in zip(sub, chunk_shape))
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=sub, dtype=np.uint8)
+    t0 = time.perf_counter()
+    out, _, parts = O.infer_chunk(img, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
+                                  framework="pytorch", model=model, return_parts=True)
+    dt = time.perf_counter() - t0
+    return dt / len(parts["slices"]), len(parts["slices"]), sub
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CFB_BENCH_WORKLOAD", "1024"), choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-size", type=int, default=int(os.environ.get("CFB_BENCH_BATCH", 4)))
+    ap.add_argument("--precision", default=os.environ.get("CHUNKFLOW_B200_PRECISION"))
+    ap.add_argument("--cpu-sample-patches", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    chunk_shape, patch, overlap = WORKLOADS[args.workload]
+    nvox = int(np.prod(chunk_shape))
+    P = patch_count(chunk_shape, patch, overlap)
+    threads = os.cpu_count() or 1
+    config = {"workload": f"{'x'.join(map(str, chunk_shape))} uint8 chunk per GPU, 3-ch affinity UNet3L(16,32,64), "
+                          f"patch {'x'.join(map(str, patch))} overlap {'x'.join(map(str, overlap))}, mask_output_chunk",
+              "patches_per_chunk": P, "batch_size": args.batch_size, "chunks": world,
+              "l2_policy": "inputs and outputs (1 GB + 12.9 GB per step) are far larger than the 126 MB L2",
+              "parallelism": f"{world} independent chunk(s), one per GPU, no collective"}
+
+    if args.impl == "reference":
+        # The reference's own CPU algorithm on the host cores (oracle port; /root/reference does not travel).
+        if rank != 0:
+            return
+        per_step = []
+        for i in range(args.warmup + args.steps):
+            spp, n, sub = cpu_reference_sample(chunk_shape, patch, overlap, args.cpu_sample_patches, 20260922 + i, threads)
+            if i >= args.warmup:
+                per_step.append(spp)
+        spp = float(np.mean(per_step))
+        value = nvox / (spp * P) / 1e6
+        sample = (f"{n} patches of {'x'.join(map(str, patch))} (sub-chunk {'x'.join(map(str, sub))}) per step incl. numpy extract/"
+                  f"blend/normalise; extrapolated by patch count to {P} patches")
+        print(json.dumps({
+            "impl": "reference", "metric": "Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * n * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from chunkflow_b200 import Chunk, Inferencer
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pin_t, host_in = synthetic_chunk(chunk_shape, 20260922 + rank)
+    inf = Inferencer(MODEL_FILE, None, patch, output_patch_overlap=overlap, num_output_channels=3, framework="b200",
+                     batch_size=args.batch_size, mask_output_chunk=True, device=local_rank, precision=args.precision)
+    eng = inf.engine
+    out_shape = eng.output_shape(chunk_shape)
+    d_in = torch.from_numpy(host_in).cuda(non_blocking=False) if pin_t is None else pin_t.cuda()
+    d_out = torch.empty(out_shape, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        eng.infer_chunk_device(d_in.data_ptr(), np.uint8, chunk_shape, d_out.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    launches = eng.last_timing()["launches"]
+    value = nvox * world * args.steps / (ms / 1e3) / 1e6
+
+    # ---- per-kernel-class roofline: one extra profiled step (CUDA events around every launch, same stream)
+    eng.set_profiling(True)
+    step_device()
+    torch.cuda.synchronize()
+    layers = eng.layer_timing()
+    eng.set_profiling(False)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    conv_ms = sum(layers[k][0] for k in CONV3_FLOP if k in layers)
+    conv_launches = sum(layers[k][1] for k in CONV3_FLOP if k in layers)
+    conv_flop = sum(CONV3_FLOP.values()) * P * int(np.prod(patch))
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "conv3x3x3 stack (all 10 layers, one kernel class)",
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
+                "traffic": None, "launches": conv_launches, "ms_per_chunk": conv_ms,
+                "algorithmic_flop_per_chunk": conv_flop}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    pv = P * int(np.prod(patch))
+    mem = {}
+    for name, bytes_per in (("extract", 5 * pv), ("blend", 36 * pv)):
+        if name in layers and layers[name][0] > 0:
+            gbs = bytes_per / (layers[name][0] / 1e3) / 1e9
+            mem[name] = {"ms_per_chunk": layers[name][0], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+    step_ms = {k: round(v[0], 3) for k, v in layers.items()}
+
+    # ---- end to end through the public API: host uint8 chunk in -> host float32 affinity map out
+    e2e = None
+    if not args.no_e2e:
+        pin_out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
+        host_out = pin_out.numpy()
+        chunk = Chunk(host_in)
+        inf(chunk, output_buffer=host_out)  # warm-up (allocates the staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            inf(chunk, output_buffer=host_out)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = {"value": nvox * world * args.steps / dt / 1e6, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(host_in.nbytes),
+               "d2h_bytes_per_step": int(host_out.nbytes), "ms_per_step": dt / args.steps * 1e3,
+               "timing_of_last_step_ms": {k: round(v, 3) for k, v in inf.timing.items()}}
+        del pin_out
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        spp, n, sub = cpu_reference_sample(chunk_shape, patch, overlap, args.cpu_sample_patches, 20260922, threads)
+        cpu = {"value": nvox / (spp * P) / 1e6, "unit": "Mvoxels/s", "cores": threads, "kind": "port",
+               "sample": f"{n} patches of {'x'.join(map(str, patch))} (sub-chunk {'x'.join(map(str, sub))}), torch-CPU network + "
+                         f"numpy extract/blend/normalise, {spp:.3f} s/patch extrapolated to {P} patches"}
+
+    if rank == 0:
+        precision = {0: "f32 (FFMA, CUDA cores)", 1: "f16x3 hi/lo split on tcgen05, f32 accumulate",
+                     2: "f16 on tcgen05, f32 accumulate"}[eng.params.precision]
+        print(json.dumps({
+            "metric": "Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if eng.params.precision == 0 else "f16", "precision_mode": precision,
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * args.steps,
+            "roofline": roofline, "memory_kernels": mem, "kernel_ms_per_chunk": step_ms, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,276 @@
+"""ctypes binding of ``include/chunkflow_b200.h`` (the C-ABI of the CUDA hot path).
+
+The library is loaded lazily and LOUDLY: if ``libchunkflow_b200.so`` is missing (and
+cannot be built) or no CUDA device is present, every compute entry point raises --
+there is no CPU fallback in the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+FRAMEWORK_UNET3L, FRAMEWORK_IDENTITY = 0, 1
+PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA = 0, 1, 2
+DTYPE_U8, DTYPE_F32 = 0, 1
+
+# every symbol include/chunkflow_b200.h declares
+EXPORTS = (
+    "cfb_last_error", "cfb_version", "cfb_device_count", "cfb_create", "cfb_destroy", "cfb_device_name",
+    "cfb_set_weight", "cfb_commit_weights", "cfb_patch_mask", "cfb_patch_grid", "cfb_output_shape",
+    "cfb_infer_chunk_device", "cfb_infer_chunk_host", "cfb_infer_slab_device", "cfb_normalize_device",
+    "cfb_patch_forward_host", "cfb_make_patch_mask", "cfb_plugin_begin", "cfb_plugin_extract", "cfb_plugin_blend",
+    "cfb_plugin_end", "cfb_last_timing", "cfb_set_profiling", "cfb_layer_timing", "cfb_debug_net_forward_host", "cfb_debug_conv3_host",
+)
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("framework", C.c_int32), ("precision", C.c_int32),
+        ("input_patch_size", C.c_int32 * 3), ("output_patch_size", C.c_int32 * 3),
+        ("output_patch_overlap", C.c_int32 * 3), ("output_crop_margin", C.c_int32 * 3),
+        ("num_input_channels", C.c_int32), ("num_output_channels", C.c_int32), ("batch_size", C.c_int32),
+        ("mask_output_chunk", C.c_int32), ("augment", C.c_int32), ("has_myelin_threshold", C.c_int32),
+        ("mask_myelin_threshold", C.c_float), ("check_output_range", C.c_int32),
+    ]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"chunkflow_b200 native error {code}: {message}")
+        self.code = code
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    from .build import LIB_PATH
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building in-tree first if the sources are newer) the native library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    from .build import build_native, LIB_PATH
+    path = LIB_PATH
+    try:
+        path = build_native()
+    except Exception as exc:  # no nvcc on this box: use the prebuilt .so that travelled with the tree
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "chunkflow_b200: the CUDA extension libchunkflow_b200.so is missing and could not be built "
+                f"({exc}); there is no CPU fallback") from exc
+    lib = C.CDLL(path)
+    vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_float)
+    lib.cfb_last_error.restype = C.c_char_p
+    lib.cfb_device_name.restype = C.c_char_p
+    lib.cfb_device_name.argtypes = [vp]
+    lib.cfb_version.restype = C.c_int
+    lib.cfb_device_count.restype = C.c_int
+    lib.cfb_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    lib.cfb_destroy.argtypes = [vp]
+    lib.cfb_set_weight.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.cfb_commit_weights.argtypes = [vp]
+    lib.cfb_patch_mask.argtypes = [vp, vp]
+    lib.cfb_patch_grid.argtypes = [vp, i64, i64, i64, C.POINTER(i64), vp, i64]
+    lib.cfb_output_shape.argtypes = [vp, i64, i64, i64, C.POINTER(i64 * 4)]
+    lib.cfb_infer_chunk_device.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp]
+    lib.cfb_infer_chunk_host.argtypes = [vp, vp, i32, i64, i64, i64, vp]
+    lib.cfb_infer_slab_device.argtypes = [vp, vp, i32, i64, i64, i64, i64, i64, vp, vp, vp]
+    lib.cfb_normalize_device.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
+    lib.cfb_patch_forward_host.argtypes = [vp, vp, i32, vp]
+    lib.cfb_make_patch_mask.argtypes = [C.POINTER(i32 * 3), C.POINTER(i32 * 3), vp]
+    lib.cfb_plugin_begin.argtypes = [vp, vp, i32, i64, i64, i64]
+    lib.cfb_plugin_extract.argtypes = [vp, i64, i32, vp]
+    lib.cfb_plugin_blend.argtypes = [vp, i64, i32, vp]
+    lib.cfb_plugin_end.argtypes = [vp, vp]
+    lib.cfb_last_timing.argtypes = [vp, C.POINTER(C.c_float * 5), C.POINTER(i64)]
+    lib.cfb_set_profiling.argtypes = [vp, i32]
+    lib.cfb_layer_timing.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp]
+    lib.cfb_debug_net_forward_host.argtypes = [vp, vp, vp]
+    lib.cfb_debug_conv3_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("cfb_version", "cfb_device_count"):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != OK:
+        raise NativeError(code, load().cfb_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def make_patch_mask(patch_size, overlap) -> np.ndarray:
+    """fp32 bump/patch mask built by the native library (no GPU needed)."""
+    ps = (C.c_int32 * 3)(*[int(v) for v in patch_size])
+    ov = (C.c_int32 * 3)(*[int(v) for v in overlap])
+    out = np.empty(tuple(int(v) for v in patch_size), np.float32)
+    check(load().cfb_make_patch_mask(C.byref(ps), C.byref(ov), _ptr(out)))
+    return out
+
+
+class Engine:
+    """RAII wrapper of a ``cfb_handle``."""
+
+    def __init__(self, *, input_patch_size, output_patch_size, output_patch_overlap, output_crop_margin,
+                 num_input_channels=1, num_output_channels=3, batch_size=1, mask_output_chunk=True,
+                 framework=FRAMEWORK_UNET3L, precision=PRECISION_F32_SIMT, device=0, augment=False,
+                 mask_myelin_threshold=None, check_output_range=True):
+        self._h = C.c_void_p()
+        self._lib = load()
+        p = Params()
+        p.struct_size = C.sizeof(Params)
+        p.device, p.framework, p.precision = int(device), int(framework), int(precision)
+        p.input_patch_size[:] = [int(v) for v in input_patch_size]
+        p.output_patch_size[:] = [int(v) for v in output_patch_size]
+        p.output_patch_overlap[:] = [int(v) for v in output_patch_overlap]
+        p.output_crop_margin[:] = [int(v) for v in output_crop_margin]
+        p.num_input_channels, p.num_output_channels = int(num_input_channels), int(num_output_channels)
+        p.batch_size, p.mask_output_chunk, p.augment = int(batch_size), int(bool(mask_output_chunk)), int(bool(augment))
+        p.has_myelin_threshold = int(mask_myelin_threshold is not None)
+        p.mask_myelin_threshold = float(mask_myelin_threshold or 0.0)
+        p.check_output_range = int(bool(check_output_range))
+        self.params = p
+        self.input_patch_size = tuple(p.input_patch_size)
+        self.output_patch_size = tuple(p.output_patch_size)
+        self.num_output_channels = p.num_output_channels
+        check(self._lib.cfb_create(C.byref(p), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.cfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @property
+    def device_name(self) -> str:
+        return self._lib.cfb_device_name(self._h).decode()
+
+    def load_state_dict(self, state: dict) -> None:
+        for name, tensor in state.items():
+            a = np.ascontiguousarray(np.asarray(tensor, dtype=np.float32))
+            check(self._lib.cfb_set_weight(self._h, name.encode(), _ptr(a), a.size))
+        check(self._lib.cfb_commit_weights(self._h))
+
+    def patch_mask(self) -> np.ndarray:
+        out = np.empty(self.output_patch_size, np.float32)
+        check(self._lib.cfb_patch_mask(self._h, _ptr(out)))
+        return out
+
+    def patch_grid(self, chunk_zyx) -> np.ndarray:
+        n = C.c_int64()
+        cz, cy, cx = (int(v) for v in chunk_zyx)
+        check(self._lib.cfb_patch_grid(self._h, cz, cy, cx, C.byref(n), None, 0))
+        starts = np.empty((n.value, 3), np.int32)
+        check(self._lib.cfb_patch_grid(self._h, cz, cy, cx, C.byref(n), _ptr(starts), n.value))
+        return starts
+
+    def output_shape(self, chunk_zyx) -> tuple:
+        out = (C.c_int64 * 4)()
+        check(self._lib.cfb_output_shape(self._h, *(int(v) for v in chunk_zyx), C.byref(out)))
+        return tuple(out)
+
+    @staticmethod
+    def _dtype_code(dtype) -> int:
+        if np.dtype(dtype) == np.uint8:
+            return DTYPE_U8
+        if np.dtype(dtype) == np.float32:
+            return DTYPE_F32
+        raise TypeError(f"input chunk dtype {dtype} is not supported on the device (uint8 or float32)")
+
+    def infer_chunk_host(self, chunk: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        chunk = np.ascontiguousarray(chunk)
+        if chunk.ndim != 3:
+            raise ValueError("expected a (z, y, x) chunk")
+        shape = self.output_shape(chunk.shape)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        assert out.shape == shape and out.dtype == np.float32 and out.flags.c_contiguous
+        check(self._lib.cfb_infer_chunk_host(self._h, _ptr(chunk), self._dtype_code(chunk.dtype), *chunk.shape, _ptr(out)))
+        return out
+
+    def infer_chunk_device(self, d_in: int, dtype, chunk_zyx, d_out: int, stream: int = 0) -> None:
+        check(self._lib.cfb_infer_chunk_device(self._h, C.c_void_p(d_in), self._dtype_code(dtype),
+                                               *(int(v) for v in chunk_zyx), C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def infer_slab_device(self, d_in: int, dtype, chunk_zyx, zrow_begin: int, zrow_end: int, d_out: int, d_weight: int,
+                          stream: int = 0) -> None:
+        check(self._lib.cfb_infer_slab_device(self._h, C.c_void_p(d_in), self._dtype_code(dtype),
+                                              *(int(v) for v in chunk_zyx), int(zrow_begin), int(zrow_end),
+                                              C.c_void_p(d_out), C.c_void_p(d_weight), C.c_void_p(stream)))
+
+    def normalize_device(self, d_out: int, d_weight: int, czyx, stream: int = 0) -> None:
+        check(self._lib.cfb_normalize_device(self._h, C.c_void_p(d_out), C.c_void_p(d_weight),
+                                             *(int(v) for v in czyx), C.c_void_p(stream)))
+
+    def patch_forward_host(self, patches: np.ndarray) -> np.ndarray:
+        patches = np.ascontiguousarray(patches, dtype=np.float32)
+        b = patches.shape[0]
+        out = np.empty((b, self.num_output_channels) + self.output_patch_size, np.float32)
+        check(self._lib.cfb_patch_forward_host(self._h, _ptr(patches), b, _ptr(out)))
+        return out
+
+    # plugin level (user-supplied patch backends)
+    def plugin_begin(self, chunk: np.ndarray) -> None:
+        chunk = np.ascontiguousarray(chunk)
+        check(self._lib.cfb_plugin_begin(self._h, _ptr(chunk), self._dtype_code(chunk.dtype), *chunk.shape))
+
+    def plugin_extract(self, first: int, nb: int, out: np.ndarray) -> None:
+        assert out.dtype == np.float32 and out.flags.c_contiguous
+        check(self._lib.cfb_plugin_extract(self._h, int(first), int(nb), _ptr(out)))
+
+    def plugin_blend(self, first: int, nb: int, masked: np.ndarray) -> None:
+        masked = np.ascontiguousarray(masked, dtype=np.float32)
+        check(self._lib.cfb_plugin_blend(self._h, int(first), int(nb), _ptr(masked)))
+
+    def plugin_end(self, out: np.ndarray) -> None:
+        check(self._lib.cfb_plugin_end(self._h, _ptr(out)))
+
+    def last_timing(self) -> dict:
+        ms = (C.c_float * 5)()
+        n = C.c_int64()
+        check(self._lib.cfb_last_timing(self._h, C.byref(ms), C.byref(n)))
+        return dict(total_ms=ms[0], convnet_ms=ms[1], blend_normalize_ms=ms[2], h2d_ms=ms[3], d2h_ms=ms[4],
+                    launches=n.value)
+
+    def set_profiling(self, enabled: bool) -> None:
+        check(self._lib.cfb_set_profiling(self._h, int(bool(enabled))))
+
+    def layer_timing(self) -> dict:
+        """kernel class -> (total ms, launches) since profiling was enabled."""
+        cap = 64
+        names = (C.c_char * 32 * cap)()
+        ms = (C.c_float * cap)()
+        launches = (C.c_int64 * cap)()
+        n = C.c_int32()
+        check(self._lib.cfb_layer_timing(self._h, cap, C.byref(n), C.cast(names, C.c_void_p), C.cast(ms, C.c_void_p),
+                                         C.cast(launches, C.c_void_p)))
+        return {names[i].value.decode(): (float(ms[i]), int(launches[i])) for i in range(n.value)}
+
+    def debug_net_forward(self, patch: np.ndarray, cnet: int) -> np.ndarray:
+        patch = np.ascontiguousarray(patch, dtype=np.float32)
+        out = np.empty((cnet,) + self.input_patch_size, np.float32)
+        check(self._lib.cfb_debug_net_forward_host(self._h, _ptr(patch), _ptr(out)))
+        return out
+
+    def debug_conv3(self, x: np.ndarray, w: np.ndarray, b: np.ndarray, relu: bool) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32); w = np.ascontiguousarray(w, np.float32); b = np.ascontiguousarray(b, np.float32)
+        cin, z, y, xx = x.shape
+        cout = w.shape[0]
+        out = np.empty((cout, z, y, xx), np.float32)
+        check(self._lib.cfb_debug_conv3_host(self._h, _ptr(x), cin, z, y, xx, _ptr(w), _ptr(b), cout, int(relu), _ptr(out)))
+        return out

@@ -1,0 +1,221 @@
+// Device-side 3-level U-Net: weight packing, workspace and layer dispatch.
+#include "network.cuh"
+
+#include "chunkflow_b200.h"
+#include "kernels_memory.cuh"
+#include "kernels_simt.cuh"
+
+namespace cfb {
+
+namespace {
+struct Spec {
+  const char* name;
+  int cin, cout, taps;  // taps: 27 conv3, 4 convT, 1 head
+};
+// execution order; cout -1 = head (num channels from the weight tensor)
+const Spec kSpecs[] = {
+    {"enc0.0", 1, 16, 27},  {"enc0.2", 16, 16, 27}, {"enc1.0", 16, 32, 27}, {"enc1.2", 32, 32, 27},
+    {"enc2.0", 32, 64, 27}, {"enc2.2", 64, 64, 27}, {"up1", 64, 32, 4},     {"dec1.0", 64, 32, 27},
+    {"dec1.2", 32, 32, 27}, {"up0", 32, 16, 4},     {"dec0.0", 32, 16, 27}, {"dec0.2", 16, 16, 27},
+    {"head", 16, -1, 1},
+};
+}  // namespace
+
+void Network::configure(int precision, Int3 patch, int batch) {
+  if (precision != CFB_PRECISION_F32_SIMT && precision != CFB_PRECISION_F16X3_UMMA && precision != CFB_PRECISION_F16_UMMA)
+    throw std::invalid_argument("unknown precision mode");
+  if (precision != CFB_PRECISION_F32_SIMT)
+    throw std::runtime_error("tcgen05 precision modes are not built into this library yet");
+  precision_ = precision;
+  patch_ = patch;
+  batch_ = batch;
+}
+
+void Network::release() {
+  for (void* p : owned_) cudaFree(p);
+  owned_.clear();
+  for (auto& kv : layers_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+  layers_.clear();
+  for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
+  prof_pool_.clear();
+  ready_ = false;
+  buf_in_ = nullptr;
+  e0a_ = nullptr;
+}
+
+float* Network::patch_input_buffer(int nb) {
+  if (nb > batch_) throw std::invalid_argument("batch larger than configured");
+  if (!buf_in_) {
+    CFB_CUDA(cudaMalloc(&buf_in_, (size_t)vol(patch_) * batch_ * sizeof(float)));
+    owned_.push_back(buf_in_);
+  }
+  return buf_in_;
+}
+
+void Network::allocate() {
+  if (e0a_) return;
+  const int64_t v0 = vol(patch_), v1 = v0 / 4, v2 = v0 / 16;
+  auto alloc = [&](int64_t floats) {
+    float* p = nullptr;
+    CFB_CUDA(cudaMalloc(&p, (size_t)floats * batch_ * sizeof(float)));
+    owned_.push_back(p);
+    return p;
+  };
+  patch_input_buffer(1);
+  e0a_ = alloc(16 * v0); e0_ = alloc(16 * v0); p0_ = alloc(16 * v1);
+  e1a_ = alloc(32 * v1); e1_ = alloc(32 * v1); p1_ = alloc(32 * v2);
+  e2a_ = alloc(64 * v2); e2_ = alloc(64 * v2);
+  u1_ = alloc(32 * v1); d1a_ = alloc(32 * v1); d1_ = alloc(32 * v1);
+  u0_ = alloc(16 * v0); d0a_ = alloc(16 * v0); d0_ = alloc(16 * v0);
+  net_out_ = alloc((int64_t)std::max(cnet_, 1) * v0);
+}
+
+bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int num_output_channels, std::string& err) {
+  ready_ = false;
+  for (auto& kv : layers_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+  layers_.clear();
+  for (const Spec& sp : kSpecs) {
+    const std::string wn = std::string(sp.name) + ".weight", bn = std::string(sp.name) + ".bias";
+    auto wi = host_w.find(wn), bi = host_w.find(bn);
+    if (wi == host_w.end() || bi == host_w.end()) { err = "missing tensor " + (wi == host_w.end() ? wn : bn); return false; }
+    int cout = sp.cout;
+    if (cout < 0) {
+      if (wi->second.size() % sp.cin) { err = "head.weight has a wrong size"; return false; }
+      cout = (int)(wi->second.size() / sp.cin);
+      cnet_ = cout;
+    }
+    if ((int64_t)wi->second.size() != (int64_t)sp.cin * cout * sp.taps) { err = wn + " has a wrong size"; return false; }
+    if ((int)bi->second.size() != cout) { err = bn + " has a wrong size"; return false; }
+    ConvLayer L;
+    L.name = sp.name; L.cin = sp.cin; L.cout = cout;
+    CFB_CUDA(cudaMalloc(&L.w, wi->second.size() * sizeof(float)));
+    CFB_CUDA(cudaMalloc(&L.bias, bi->second.size() * sizeof(float)));
+    CFB_CUDA(cudaMemcpy(L.w, wi->second.data(), wi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CFB_CUDA(cudaMemcpy(L.bias, bi->second.data(), bi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
+    layers_[sp.name] = L;
+  }
+  if (num_output_channels > cnet_) { err = "the network produces fewer channels than num_output_channels"; return false; }
+  if (cnet_ > 8) { err = "at most 8 network output channels are supported"; return false; }
+  allocate();
+  ready_ = true;
+  return true;
+}
+
+void Network::set_profiling(bool on) {
+  profiling_ = on;
+  std::vector<std::string> n; std::vector<float> m; std::vector<int64_t> l;
+  layer_timing(n, m, l);  // drain
+  prof_names_.clear(); prof_ms_.clear(); prof_launches_.clear();
+}
+
+void Network::prof_begin(const char* name, cudaStream_t s) {
+  if (!profiling_) return;
+  int id = -1;
+  for (size_t i = 0; i < prof_names_.size(); ++i) if (prof_names_[i] == name) id = (int)i;
+  if (id < 0) { id = (int)prof_names_.size(); prof_names_.push_back(name); prof_ms_.push_back(0.f); prof_launches_.push_back(0); }
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!prof_pool_.empty()) { e = prof_pool_.back(); prof_pool_.pop_back(); } else { CFB_CUDA(cudaEventCreate(&e)); }
+    return e;
+  };
+  Span sp{id, get(), get()};
+  CFB_CUDA(cudaEventRecord(sp.a, s));
+  prof_spans_.push_back(sp);
+  prof_cur_ = (int)prof_spans_.size() - 1;
+}
+
+void Network::prof_end(cudaStream_t s) {
+  if (!profiling_ || prof_cur_ < 0) return;
+  CFB_CUDA(cudaEventRecord(prof_spans_[prof_cur_].b, s));
+  prof_cur_ = -1;
+}
+
+void Network::layer_timing(std::vector<std::string>& names, std::vector<float>& ms, std::vector<int64_t>& launches) {
+  for (Span& sp : prof_spans_) {
+    CFB_CUDA(cudaEventSynchronize(sp.b));
+    float t = 0.f;
+    CFB_CUDA(cudaEventElapsedTime(&t, sp.a, sp.b));
+    prof_ms_[sp.id] += t;
+    prof_launches_[sp.id] += 1;
+    prof_pool_.push_back(sp.a);
+    prof_pool_.push_back(sp.b);
+  }
+  prof_spans_.clear();
+  names = prof_names_; ms = prof_ms_; launches = prof_launches_;
+}
+
+int Network::forward(int nb, cudaStream_t s) {
+  const Int3 s0 = patch_, s1{patch_.z, patch_.y / 2, patch_.x / 2}, s2{patch_.z, patch_.y / 4, patch_.x / 4};
+  auto conv = [&](const char* name, const float* a, int ca, const float* b, int cb, float* out, Int3 sz) {
+    const ConvLayer& L = layers_.at(name);
+    prof_begin(name, s);
+    launch_conv3_f32(a, ca, b, cb, L.w, L.bias, out, L.cout, nb, sz, /*relu=*/true, s);
+    prof_end(s);
+  };
+  conv("enc0.0", buf_in_, 1, nullptr, 0, e0a_, s0);
+  conv("enc0.2", e0a_, 16, nullptr, 0, e0_, s0);
+  prof_begin("pool0", s); launch_maxpool_f32(e0_, p0_, 16, nb, s0, s); prof_end(s);
+  conv("enc1.0", p0_, 16, nullptr, 0, e1a_, s1);
+  conv("enc1.2", e1a_, 32, nullptr, 0, e1_, s1);
+  prof_begin("pool1", s); launch_maxpool_f32(e1_, p1_, 32, nb, s1, s); prof_end(s);
+  conv("enc2.0", p1_, 32, nullptr, 0, e2a_, s2);
+  conv("enc2.2", e2a_, 64, nullptr, 0, e2_, s2);
+  { const ConvLayer& L = layers_.at("up1"); prof_begin("up1", s); launch_convT_f32(e2_, L.w, L.bias, u1_, 64, 32, nb, s2, s); prof_end(s); }
+  conv("dec1.0", u1_, 32, e1_, 32, d1a_, s1);  // torch.cat([up1, enc1])
+  conv("dec1.2", d1a_, 32, nullptr, 0, d1_, s1);
+  { const ConvLayer& L = layers_.at("up0"); prof_begin("up0", s); launch_convT_f32(d1_, L.w, L.bias, u0_, 32, 16, nb, s1, s); prof_end(s); }
+  conv("dec0.0", u0_, 16, e0_, 16, d0a_, s0);  // torch.cat([up0, enc0])
+  conv("dec0.2", d0a_, 16, nullptr, 0, d0_, s0);
+  { const ConvLayer& L = layers_.at("head"); prof_begin("head", s); launch_head_sigmoid_f32(d0_, L.w, L.bias, net_out_, 16, cnet_, nb, s0, s); prof_end(s); }
+  return 15;
+}
+
+int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s) {
+  if (nb > batch_) throw std::invalid_argument("batch larger than configured");
+  prof_begin("extract", s);
+  launch_extract_patches(chunk, in_dtype, cs, patches, nb, patch_, buf_in_, s);
+  prof_end(s);
+  return 1 + forward(nb, s);
+}
+
+int Network::forward_from_host_patches(const float* h_patches, int nb, cudaStream_t s) {
+  if (nb > batch_) throw std::invalid_argument("batch larger than configured");
+  CFB_CUDA(cudaMemcpyAsync(buf_in_, h_patches, (size_t)nb * vol(patch_) * sizeof(float), cudaMemcpyHostToDevice, s));
+  return forward(nb, s);
+}
+
+int Network::blend(Int3 op, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out, int channels,
+                   Int3 out_size, cudaStream_t s) {
+  prof_begin("blend", s);
+  launch_blend_patches(net_out_, cnet_, patch_, op, crop, mask, patches, nb, out, channels, out_size, 1.0f, s);
+  prof_end(s);
+  return 1;
+}
+
+void Network::crop_mask(Int3 op, Int3 crop, const float* mask, int nb, float* dst, int channels, cudaStream_t s) {
+  launch_crop_mask(net_out_, cnet_, patch_, op, crop, mask, nb, dst, channels, /*repeat=*/false, s);
+}
+
+void Network::copy_raw_output_to_host(float* h_out, cudaStream_t s) {
+  CFB_CUDA(cudaMemcpyAsync(h_out, net_out_, (size_t)cnet_ * vol(patch_) * sizeof(float), cudaMemcpyDeviceToHost, s));
+}
+
+int Network::debug_conv3(const float* h_in, int cin, Int3 size, const float* h_w, const float* h_b, int cout, bool relu,
+                         float* h_out, cudaStream_t s) {
+  float *d_in = nullptr, *d_w = nullptr, *d_b = nullptr, *d_out = nullptr;
+  const int64_t v = vol(size);
+  CFB_CUDA(cudaMalloc(&d_in, (size_t)cin * v * 4));
+  CFB_CUDA(cudaMalloc(&d_w, (size_t)cout * cin * 27 * 4));
+  CFB_CUDA(cudaMalloc(&d_b, (size_t)cout * 4));
+  CFB_CUDA(cudaMalloc(&d_out, (size_t)cout * v * 4));
+  CFB_CUDA(cudaMemcpyAsync(d_in, h_in, (size_t)cin * v * 4, cudaMemcpyHostToDevice, s));
+  CFB_CUDA(cudaMemcpyAsync(d_w, h_w, (size_t)cout * cin * 27 * 4, cudaMemcpyHostToDevice, s));
+  CFB_CUDA(cudaMemcpyAsync(d_b, h_b, (size_t)cout * 4, cudaMemcpyHostToDevice, s));
+  launch_conv3_f32(d_in, cin, nullptr, 0, d_w, d_b, d_out, cout, 1, size, relu, s);
+  CFB_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)cout * v * 4, cudaMemcpyDeviceToHost, s));
+  CFB_CUDA(cudaStreamSynchronize(s));
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_b); cudaFree(d_out);
+  return CFB_OK;
+}
+
+}  // namespace cfb

@@ -1,0 +1,177 @@
+/*
+ * chunkflow_b200 -- C-ABI of the B200-native `inference` hot path.
+ *
+ * Drop-in boundary for chunkflow's overlap-tile convnet inference.  The reference is
+ * pure Python; each entry point names the reference interface it replaces
+ * (paths relative to the reference tree, v1.1.7):
+ *
+ *   cfb_create / cfb_destroy      Inferencer.__init__ / __exit__
+ *                                 chunkflow/flow/divid_conquer/inferencer.py:36-171,177-181
+ *   cfb_set_weight / cfb_commit_weights
+ *                                 PyTorch.__init__ weight loading
+ *                                 chunkflow/flow/divid_conquer/patch/pytorch.py:48-63
+ *   cfb_patch_mask                PatchMask / make_patch_mask
+ *                                 chunkflow/flow/divid_conquer/patch/patch_mask.py:6-48
+ *   cfb_patch_grid                Inferencer._construct_patch_slices_list   inferencer.py:255-292
+ *   cfb_output_shape              Inferencer._update_parameters_for_input_chunk   inferencer.py:183-204
+ *   cfb_infer_chunk_device/_host  Inferencer.__call__   inferencer.py:360-479
+ *                                 (Chunk.cutout chunk/base.py:761-781, Chunk.blend chunk/base.py:792-807,
+ *                                  PyTorch.__call__ patch/pytorch.py:98-119)
+ *   cfb_patch_forward_host        PatchInferencer.__call__ plugin level
+ *                                 patch/pytorch.py:98-119, patch/universal.py:60-69, patch/identity.py:30-51
+ *   cfb_device_name               Inferencer.compute_device   inferencer.py:173-175
+ *
+ * Plain pointers and sizes only -- no torch types.  Device pointers are raw CUDA device
+ * addresses (e.g. torch.Tensor.data_ptr()) owned by the caller.  All functions return
+ * CFB_OK (0) or a negative error code; cfb_last_error() returns the message of the last
+ * failure on the calling thread.  There is NO CPU fallback: without a CUDA device every
+ * compute entry point fails with CFB_ERR_CUDA.
+ */
+#ifndef CHUNKFLOW_B200_H_
+#define CHUNKFLOW_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFB_OK 0
+#define CFB_ERR_INVALID_ARGUMENT (-1)
+#define CFB_ERR_CUDA (-2)
+#define CFB_ERR_WEIGHTS (-3)
+#define CFB_ERR_OUTPUT_RANGE (-4) /* some output >= 1.0001 (reference inferencer.py:465-466) */
+#define CFB_ERR_UNSUPPORTED (-5)
+
+/* framework: which patch backend runs on the device */
+#define CFB_FRAMEWORK_UNET3L 0   /* fixed 3-level 3D U-Net (chunkflow_b200/convnet/unet3l.py) */
+#define CFB_FRAMEWORK_IDENTITY 1 /* reference patch/identity.py: output = input patch */
+
+/* precision of the convolution stack */
+#define CFB_PRECISION_F32_SIMT 0   /* fp32 FFMA direct convolution (exact-order-free fp32) */
+#define CFB_PRECISION_F16X3_UMMA 1 /* tcgen05 fp16 hi/lo split, fp32 accumulate (~fp32 accuracy) */
+#define CFB_PRECISION_F16_UMMA 2   /* tcgen05 single-pass fp16, fp32 accumulate (reference --dtype float16) */
+
+/* dtype of the input chunk */
+#define CFB_DTYPE_U8 0
+#define CFB_DTYPE_F32 1
+
+typedef struct cfb_engine* cfb_handle;
+
+typedef struct cfb_params {
+  int32_t struct_size;             /* = sizeof(cfb_params), for ABI checks */
+  int32_t device;                  /* CUDA device ordinal */
+  int32_t framework;               /* CFB_FRAMEWORK_* */
+  int32_t precision;               /* CFB_PRECISION_* */
+  int32_t input_patch_size[3];     /* z, y, x */
+  int32_t output_patch_size[3];    /* z, y, x (<= input; crop margin = (in-out)/2) */
+  int32_t output_patch_overlap[3]; /* z, y, x */
+  int32_t output_crop_margin[3];   /* z, y, x: margin of the output chunk that is dropped */
+  int32_t num_input_channels;      /* must be 1 */
+  int32_t num_output_channels;     /* channels returned (network may produce more; first N kept) */
+  int32_t batch_size;              /* patches in flight per launch (scheduling hint) */
+  int32_t mask_output_chunk;       /* 1: normalise by the accumulated weight volume */
+  int32_t augment;                 /* 1: 8-fold test-time augmentation (reference transform.py) */
+  int32_t has_myelin_threshold;    /* 1: drop last channel, zero where it is >= threshold */
+  float mask_myelin_threshold;
+  int32_t check_output_range;      /* 1: fail with CFB_ERR_OUTPUT_RANGE like the reference assert */
+} cfb_params;
+
+const char* cfb_last_error(void);
+int cfb_version(void);
+/* Number of CUDA devices visible (0 if none / no driver). Never fails. */
+int cfb_device_count(void);
+
+int cfb_create(const cfb_params* params, cfb_handle* out);
+int cfb_destroy(cfb_handle h);
+/* Name of the CUDA device the engine runs on (valid until cfb_destroy). */
+const char* cfb_device_name(cfb_handle h);
+
+/* Weights: fp32 host arrays in PyTorch state_dict layout, keyed by state_dict name
+ * ("enc0.0.weight", "enc0.0.bias", ... "head.bias"). commit packs them for the kernels. */
+int cfb_set_weight(cfb_handle h, const char* name, const float* host_data, int64_t numel);
+int cfb_commit_weights(cfb_handle h);
+
+/* Device-free: fp32 patch mask for (patch z,y,x ; overlap z,y,x) into host memory
+ * (prod(patch) floats).  Replaces make_patch_mask, patch/patch_mask.py:15-48. */
+int cfb_make_patch_mask(const int32_t patch_size[3], const int32_t overlap[3], float* host_out);
+
+/* Copies the fp32 patch mask (prod(output_patch_size) floats) to host memory. */
+int cfb_patch_mask(cfb_handle h, float* host_out);
+
+/* Patch grid for a chunk of the given size: writes the number of patches and, if
+ * starts_zyx != NULL, up to `capacity` chunk-local input start triples (z,y,x per patch,
+ * z-major then y then x, last patch per axis clamped). */
+int cfb_patch_grid(cfb_handle h, int64_t cz, int64_t cy, int64_t cx,
+                   int64_t* num_patches, int32_t* starts_zyx, int64_t capacity);
+
+/* Output chunk shape (C, z, y, x) for an input chunk (z, y, x). */
+int cfb_output_shape(cfb_handle h, int64_t cz, int64_t cy, int64_t cx, int64_t out_czyx[4]);
+
+/* Whole-chunk inference, input and output resident in device memory.
+ * d_in : (cz,cy,cx) uint8 or float32, contiguous; d_out: (C,oz,oy,ox) float32.
+ * `stream` is a cudaStream_t (NULL = default stream).  Asynchronous unless
+ * check_output_range is set (the range check synchronises the stream). */
+int cfb_infer_chunk_device(cfb_handle h, const void* d_in, int32_t in_dtype,
+                           int64_t cz, int64_t cy, int64_t cx, float* d_out, void* stream);
+
+/* Same, host buffers: H2D copy of the chunk, inference, D2H copy of the result. */
+int cfb_infer_chunk_host(cfb_handle h, const void* h_in, int32_t in_dtype,
+                         int64_t cz, int64_t cy, int64_t cx, float* h_out);
+
+/* Slab variant used when one oversized chunk is split across GPUs: processes only the
+ * patches whose z-row index is in [zrow_begin, zrow_end) and leaves d_out as the
+ * UN-normalised partial sum; d_weight (oz,oy,ox) receives this slab's partial weight
+ * sum.  The caller adds the halo rows of neighbouring ranks (NCCL) and then calls
+ * cfb_normalize_device. */
+int cfb_infer_slab_device(cfb_handle h, const void* d_in, int32_t in_dtype,
+                          int64_t cz, int64_t cy, int64_t cx,
+                          int64_t zrow_begin, int64_t zrow_end,
+                          float* d_out, float* d_weight, void* stream);
+int cfb_normalize_device(cfb_handle h, float* d_out, const float* d_weight,
+                         int64_t channels, int64_t oz, int64_t oy, int64_t ox, void* stream);
+
+/* PatchInferencer plugin level: `batch` input patches (batch,1,pz,py,px) float32 in
+ * [0,1] on the host -> (batch,C,oz,oy,ox) float32 on the host, already cropped and
+ * multiplied by the patch mask (reference patch/pytorch.py:112-113). */
+int cfb_patch_forward_host(cfb_handle h, const float* h_patches, int32_t batch, float* h_out);
+
+/* Plugin level for user-supplied patch backends (`-f universal`, framework='prebuilt';
+ * reference patch/universal.py:43-69, inferencer.py:209-211,404-455).  The user's callable
+ * maps host patches to host outputs that are ALREADY cropped and bump-masked; extract,
+ * blend and normalise still run on the device:
+ *   begin   : upload the chunk, build the patch grid, zero the accumulators
+ *   extract : patches [first, first+nb) -> (nb,1,pz,py,px) float32 on the host
+ *   blend   : (nb,C,oz,oy,ox) float32 masked outputs from the host -> accumulate
+ *   end     : normalise (+ range check, myelin) and copy (C,oz,oy,ox) to the host */
+int cfb_plugin_begin(cfb_handle h, const void* h_in, int32_t in_dtype, int64_t cz, int64_t cy, int64_t cx);
+int cfb_plugin_extract(cfb_handle h, int64_t first, int32_t nb, float* h_patches);
+int cfb_plugin_blend(cfb_handle h, int64_t first, int32_t nb, const float* h_masked_outputs);
+int cfb_plugin_end(cfb_handle h, float* h_out);
+
+/* Timing of the last cfb_infer_chunk_* call, CUDA events on the work stream (ms):
+ * [0] total device time, [1] convnet kernels, [2] blend+normalise, [3] h2d, [4] d2h.
+ * Kernel launches of the last call are returned through *launches. */
+int cfb_last_timing(cfb_handle h, float ms[5], int64_t* launches);
+
+/* Per-layer profiling (tracing aid; reference keeps only wall-clock per operator,
+ * flow/flow.py:1926-1932).  When enabled every network kernel launch of the following
+ * inference calls is bracketed by CUDA events on the work stream.  cfb_layer_timing
+ * synchronises and reports, for up to `capacity` kernel classes: a name (<=31 chars),
+ * total milliseconds and launch count accumulated since profiling was enabled. */
+int cfb_set_profiling(cfb_handle h, int32_t enabled);
+int cfb_layer_timing(cfb_handle h, int32_t capacity, int32_t* count, char (*names)[32], float* ms,
+                     int64_t* launches);
+
+/* Test hook: raw network output (before crop/mask) of one host patch, (Cnet,pz,py,px). */
+int cfb_debug_net_forward_host(cfb_handle h, const float* h_patch, float* h_out);
+/* Test hook: one 3x3x3 convolution layer run through the engine's precision path.
+ * in (cin,z,y,x) fp32 host, weight (cout,cin,3,3,3), bias (cout) -> out (cout,z,y,x). */
+int cfb_debug_conv3_host(cfb_handle h, const float* h_in, int32_t cin, int32_t z, int32_t y, int32_t x,
+                         const float* h_weight, const float* h_bias, int32_t cout, int32_t relu,
+                         float* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHUNKFLOW_B200_H_ */

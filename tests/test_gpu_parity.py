@@ -1,0 +1,238 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle,
+the golden vectors of the real reference, and size-independent properties."""
+import numpy as np
+import pytest
+
+from conftest import MODEL_FILE
+from chunkflow_b200 import Chunk, _native
+from oracle import inferencer_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# identity / blend arithmetic is fp32 with atomics in arbitrary order: ~1 ulp of the sums
+BLEND_ATOL = 2e-6
+# fp32 SIMT convolutions vs torch-CPU: different summation order only
+NET_ATOL_F32 = 2e-5
+# north_star tolerance for the tensor-core path
+NET_ATOL = 1e-3
+
+
+def _inferencer(**kw):
+    from chunkflow_b200 import Inferencer
+    return Inferencer(kw.pop("model", None), kw.pop("weights", None), kw.pop("input_patch_size"), **kw)
+
+
+def test_patch_grid_through_the_c_abi(geometry):
+    for key, starts in geometry["patch_grids"].items():
+        size, patch, ov = (tuple(map(int, t.split("x"))) for t in key.split("_"))
+        eng = _native.Engine(input_patch_size=patch, output_patch_size=patch, output_patch_overlap=ov,
+                             output_crop_margin=(0, 0, 0), framework=_native.FRAMEWORK_IDENTITY)
+        assert eng.patch_grid(size).tolist() == starts, key
+        assert np.array_equal(eng.patch_mask(), O.make_patch_mask(patch, ov))
+        eng.close()
+
+
+def test_identity_nonaligned_golden(golden):
+    g = golden("identity_nonaligned.npz")
+    inf = _inferencer(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=2,
+                      batch_size=5, framework="identity", mask_output_chunk=True)
+    out = inf(Chunk(g["input"], voxel_offset=(3, 5, 7)))
+    assert tuple(out.voxel_offset) == tuple(g["voxel_offset"])
+    np.testing.assert_allclose(out.array, g["output"], rtol=0, atol=BLEND_ATOL)
+    got = [[[s.start, s.stop] for s in pair[0]] + [[s.start, s.stop] for s in pair[1]] for pair in inf.patch_slices_list]
+    assert got == g["patch_slices"].tolist()
+    assert "B200" in inf.compute_device or "NVIDIA" in inf.compute_device
+
+
+def test_identity_aligned_golden(golden):
+    g = golden("identity_aligned.npz")
+    inf = _inferencer(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=2,
+                      patch_num=(2, 2, 2), framework="identity", batch_size=3, mask_output_chunk=False)
+    out = inf(Chunk(g["input"]))
+    assert tuple(out.voxel_offset) == (2, 8, 8) and out.shape == g["output"].shape
+    np.testing.assert_allclose(out.array, g["output"], rtol=0, atol=BLEND_ATOL)
+
+
+def test_reference_test_non_aligned_input_chunk():
+    """tests/flow/divid_conquer/test_inferencer.py:141-169 at the reference's own sizes."""
+    rng = np.random.default_rng(7)
+    img = rng.integers(1, 255, size=(28 * 2 + 4 + 6, 192 * 2 + 64 + 7, 192 * 2 + 64 + 9), dtype=np.uint8)
+    inf = _inferencer(input_patch_size=(32, 256, 256), output_patch_overlap=(4, 64, 64), num_output_channels=2,
+                      batch_size=5, framework="identity", mask_output_chunk=True)
+    out = inf(Chunk(img))
+    np.testing.assert_allclose(img.astype(np.float32) / 255, out.array[0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out.array[0], out.array[1], rtol=0, atol=BLEND_ATOL)
+    o, _ = O.infer_chunk(img, input_patch_size=(32, 256, 256), output_patch_overlap=(4, 64, 64), num_output_channels=2,
+                         framework="identity")
+    np.testing.assert_allclose(out.array, o, rtol=0, atol=BLEND_ATOL)
+
+
+def test_reference_test_aligned_patch_num_float16():
+    """test_inferencer.py:60-95: dtype float16, batch 5, two channels, aligned, no chunk mask."""
+    rng = np.random.default_rng(8)
+    img = rng.integers(1, 255, size=(28 * 2 + 4, 192 * 2 + 64, 192 * 2 + 64), dtype=np.uint8)
+    inf = _inferencer(input_patch_size=(32, 256, 256), output_patch_overlap=(4, 64, 64), num_output_channels=2,
+                      patch_num=(2, 2, 2), framework="identity", dtype="float16", batch_size=5, mask_output_chunk=False)
+    out = inf(Chunk(img))
+    ref = img[4:-4, 64:-64, 64:-64].astype(np.float32) / 255
+    np.testing.assert_allclose(ref, out.array[0], rtol=1e-3, atol=1e-3)
+
+
+def test_reference_test_time_augmentation_identity():
+    """test_inferencer.py:6-32."""
+    image = Chunk.create(size=(18, 224, 224), dtype="uint8")
+    inf = _inferencer(input_patch_size=(10, 128, 128), num_output_channels=3, output_patch_overlap=(2, 32, 32),
+                      input_size=(18, 224, 224), mask_output_chunk=False, framework="identity", augment=True)
+    out = inf(image)
+    assert np.all(np.isclose(image.array[2:-2, 32:-32, 32:-32], out.array[0] * 255, atol=1))
+    o, _ = O.infer_chunk(image.array, input_patch_size=(10, 128, 128), output_patch_overlap=(2, 32, 32),
+                         num_output_channels=3, framework="identity", mask_output_chunk=False, augment=True)
+    np.testing.assert_allclose(out.array, o, rtol=0, atol=BLEND_ATOL)
+
+
+def test_unet3l_golden(golden):
+    g = golden("unet3l_small.npz")
+    for batch in (1, 4):
+        inf = _inferencer(model=MODEL_FILE, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8),
+                          num_output_channels=3, batch_size=batch, framework="pytorch", mask_output_chunk=True)
+        out = inf(Chunk(g["input"]))
+        err = np.abs(out.array - g["output"]).max()
+        print("unet3l golden max-abs", err)
+        assert err <= NET_ATOL_F32
+
+
+def test_unet3l_readme_config_against_oracle(unet_model):
+    """BASELINE config #1 geometry (patch 20x256x256, overlap 4x64x64) on the sin chunk, 2 z-rows."""
+    chunk = Chunk.create(size=(36, 256, 256), dtype=np.uint8, pattern="sin")
+    inf = _inferencer(input_patch_size=(20, 256, 256), output_patch_overlap=(4, 64, 64), num_output_channels=3,
+                      batch_size=2, framework="b200", mask_output_chunk=True)
+    out = inf(chunk)
+    o, _ = O.infer_chunk(chunk.array, input_patch_size=(20, 256, 256), output_patch_overlap=(4, 64, 64),
+                         num_output_channels=3, framework="pytorch", model=unet_model)
+    err = np.abs(out.array - o).max()
+    print("config #1 geometry max-abs", err, "timing", inf.timing)
+    assert err <= NET_ATOL_F32
+    assert inf.timing["launches"] > 0
+
+
+@pytest.mark.parametrize("cin,cout,size", [(1, 16, (5, 20, 36)), (16, 16, (4, 16, 70)), (48, 32, (3, 9, 13)), (64, 64, (6, 8, 8))])
+def test_conv3_layer_against_torch(cin, cout, size):
+    import torch
+    rng = np.random.default_rng(cin * 100 + cout)
+    x = rng.standard_normal((cin,) + size).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(27 * cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    eng = _native.Engine(input_patch_size=(8, 32, 32), output_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8),
+                         output_crop_margin=(0, 0, 0), framework=_native.FRAMEWORK_IDENTITY)
+    got = eng.debug_conv3(x, w, b, relu=True)
+    ref = torch.relu(torch.nn.functional.conv3d(torch.from_numpy(x)[None], torch.from_numpy(w), torch.from_numpy(b), padding=1))[0].numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)
+
+
+def test_plugin_level_patch_inferencer(unet_model):
+    """B3: per-patch numpy API, output already cropped and masked (reference patch/pytorch.py:98-119)."""
+    from chunkflow_b200.flow.divid_conquer.patch.b200 import B200
+    rng = np.random.default_rng(11)
+    patches = rng.random((3, 1, 8, 32, 32)).astype(np.float32)
+    pi = B200(MODEL_FILE, None, (8, 32, 32), (8, 32, 32), (2, 8, 8), num_output_channels=3, batch_size=2)
+    got = pi(patches)
+    geom = O.Geometry((8, 32, 32), None, (2, 8, 8))
+    ref = np.concatenate([O.TorchPatch(geom, 3, O.make_patch_mask((8, 32, 32), (2, 8, 8)), unet_model)(p[None]) for p in patches])
+    np.testing.assert_allclose(got, ref, rtol=0, atol=NET_ATOL_F32)
+    # ... and as framework='prebuilt' inside the Inferencer (device extract/blend around a host plugin)
+    img = rng.integers(0, 256, size=(12, 40, 48), dtype=np.uint8)
+    inf = _inferencer(model=pi, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3,
+                      batch_size=2, framework="prebuilt")
+    out = inf(Chunk(img))
+    o, _ = O.infer_chunk(img, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3,
+                         framework="pytorch", model=unet_model)
+    np.testing.assert_allclose(out.array, o, rtol=0, atol=NET_ATOL_F32)
+
+
+def test_universal_plugin_file(tmp_path):
+    """`-f universal` with the reference's example plugin contract (examples/inference/universal_identity.py)."""
+    plugin = tmp_path / "universal_identity.py"
+    plugin.write_text(
+        "import numpy as np\n"
+        "class PatchInferencer:\n"
+        "    def __init__(self, model_weight_file, output_patch_mask):\n"
+        "        self.output_patch_mask = output_patch_mask\n"
+        "    @property\n"
+        "    def compute_device(self):\n"
+        "        return 'host-plugin'\n"
+        "    def __call__(self, input_patch):\n"
+        "        out = np.copy(input_patch) * self.output_patch_mask\n"
+        "        return np.repeat(out, 3, axis=1)\n")
+    image = Chunk.create(size=(36, 448, 448), dtype="uint8")
+    inf = _inferencer(model=str(plugin), input_patch_size=(20, 256, 256), output_patch_overlap=(4, 64, 64),
+                      patch_num=(2, 2, 2), framework="universal", batch_size=3, mask_output_chunk=False,
+                      num_output_channels=3)
+    out = inf(image)
+    assert inf.compute_device == "host-plugin" and out.shape == (3, 28, 320, 320)
+    np.testing.assert_allclose(image.array[4:-4, 64:-64, 64:-64].astype(np.float32) / 255, out.array[2], atol=1e-5)
+
+
+def test_edge_cases_zero_input_range_check_myelin_dry_run(unet_model):
+    kw = dict(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), batch_size=3)
+    # all-zero shortcut (reference inferencer.py:387-393): zeros even though sigmoid(net(0)) != 0
+    inf = _inferencer(model=MODEL_FILE, num_output_channels=3, framework="b200", **kw)
+    out = inf(Chunk(np.zeros((10, 40, 40), np.uint8)))
+    assert out.shape == (3, 10, 40, 40) and not out.array.any()
+    # a chunk of exactly one patch
+    one = inf(Chunk.create(size=(8, 32, 32)))
+    o, _ = O.infer_chunk(Chunk.create(size=(8, 32, 32)).array, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8),
+                         num_output_channels=3, framework="pytorch", model=unet_model)
+    np.testing.assert_allclose(one.array, o, rtol=0, atol=NET_ATOL_F32)
+    # chunk smaller than a patch: refused (reference asserts iz >= 0, inferencer.py:270-271)
+    with pytest.raises(_native.NativeError):
+        inf(Chunk.create(size=(6, 32, 32)))
+    # float input > 1 through identity trips the reference's `< 1.0001` assertion (inferencer.py:465-466)
+    ident = _inferencer(num_output_channels=1, framework="identity", **kw)
+    with pytest.raises(AssertionError):
+        ident(Chunk(np.full((10, 40, 40), 1.5, np.float32)))
+    ok = ident(Chunk(np.full((10, 40, 40), 0.25, np.float32)))
+    np.testing.assert_allclose(ok.array, 0.25, atol=BLEND_ATOL)
+    # myelin masking needs 4 channels, returns 3 (reference inferencer.py:468-477, chunk/base.py:685-689)
+    rng = np.random.default_rng(5)
+    img = rng.random((10, 40, 40)).astype(np.float32)
+    my = _inferencer(num_output_channels=4, framework="identity", mask_myelin_threshold=0.5, **kw)
+    res = my(Chunk(img))
+    assert res.shape == (3, 10, 40, 40)
+    np.testing.assert_allclose(res.array[0], np.where(img < 0.5, img, 0), atol=BLEND_ATOL)
+    # dry run returns a synthetic chunk of the output shape without touching the device path
+    dry = _inferencer(num_output_channels=2, framework="identity", dry_run=True, **kw)(Chunk.create(size=(10, 40, 40)))
+    assert dry.shape == (2, 10, 40, 40)
+    # uint16 input is normalised by its dtype maximum
+    u16 = (rng.random((10, 40, 40)) * 65535).astype(np.uint16)
+    r16 = ident(Chunk(u16))
+    np.testing.assert_allclose(r16.array[0], u16.astype(np.float32) / 65535, atol=BLEND_ATOL)
+
+
+def test_cropped_output_patch_and_crop_margin(unet_model):
+    """output_patch_size < input_patch_size with an explicit output crop margin and a global offset.
+    (The reference's own test for this is skipped upstream as 'known bug', test_inferencer.py:98-139;
+    the oracle restates the arithmetic as written.)"""
+    rng = np.random.default_rng(13)
+    img = rng.integers(1, 256, size=(2 * 6 + 4, 2 * 24 + 16, 2 * 24 + 16), dtype=np.uint8)
+    kw = dict(input_patch_size=(10, 40, 40), output_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8))
+    inf = _inferencer(num_output_channels=1, framework="identity", batch_size=5, mask_output_chunk=False,
+                      patch_num=(2, 2, 2), **kw)
+    out = inf(Chunk(img, voxel_offset=(123, 345, 567)))
+    o, off = O.infer_chunk(img, (123, 345, 567), num_output_channels=1, framework="identity", mask_output_chunk=False, **kw)
+    assert tuple(out.voxel_offset) == off and out.shape == o.shape
+    np.testing.assert_allclose(out.array, o, rtol=0, atol=BLEND_ATOL)
+
+
+def test_large_chunk_properties():
+    """Size-independent properties at a larger size than the oracle handles quickly: the blend of
+    an identity network reproduces the input (partition of unity + normalisation), is channel-
+    symmetric and idempotent across repeated calls with cached tables."""
+    rng = np.random.default_rng(17)
+    img = rng.integers(1, 255, size=(96, 600, 520), dtype=np.uint8)
+    inf = _inferencer(input_patch_size=(32, 256, 256), output_patch_overlap=(8, 64, 64), num_output_channels=3,
+                      batch_size=12, framework="identity")
+    a = inf(Chunk(img)).array
+    np.testing.assert_allclose(a[0], img.astype(np.float32) / 255, rtol=1e-5, atol=1e-5)
+    assert np.abs(a[0] - a[2]).max() <= BLEND_ATOL
+    b = inf(Chunk(img)).array
+    assert np.abs(a - b).max() <= BLEND_ATOL

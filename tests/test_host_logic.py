@@ -1,0 +1,114 @@
+"""Host logic that needs no GPU: boundary types, the native library's exports, the
+device-free patch mask, and loud failure without a CUDA device."""
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, has_gpu
+from chunkflow_b200 import Cartesian, Chunk, to_cartesian
+from chunkflow_b200 import _native
+from oracle import inferencer_oracle as O
+
+
+def test_cartesian_arithmetic_and_partial_order():
+    a = Cartesian(4, 64, 64)
+    assert a // 2 == Cartesian(2, 32, 32) and a * 2 == (8, 128, 128) and a - 1 == (3, 63, 63)
+    assert (Cartesian(20, 256, 256) - Cartesian(16, 192, 192)) // 2 == (2, 32, 32)
+    assert Cartesian(4, 64, 64) >= Cartesian(4, 64, 64)
+    assert not (Cartesian(4, 64, 1) >= Cartesian(4, 64, 64))      # every axis must hold
+    assert not (Cartesian(4, 64, 1) < Cartesian(4, 64, 64))       # ... so neither >= nor <
+    assert to_cartesian(None) is None and to_cartesian([1, 2, 3]) == Cartesian(1, 2, 3)
+    with pytest.raises((AssertionError, ValueError)):
+        to_cartesian((1, 2))
+
+
+def test_chunk_blend_clips_like_reference():
+    buf = Chunk(np.zeros((2, 6, 8, 8), np.float32), voxel_offset=(10, 20, 30))
+    patch = Chunk(np.ones((2, 4, 4, 4), np.float32), voxel_offset=(14, 26, 28))
+    buf.blend(patch)
+    ref = np.zeros((2, 6, 8, 8), np.float32)
+    O._blend(ref, (10, 20, 30), patch.array, (14, 26, 28))
+    assert np.array_equal(buf.array, ref) and buf.array.sum() == 2 * 2 * 2 * 2
+
+
+def test_chunk_cutout_ufunc_and_myelin():
+    c = Chunk(np.arange(4 * 5 * 6, dtype=np.float32).reshape(4, 5, 6), voxel_offset=(1, 2, 3), voxel_size=(40, 4, 4))
+    sub = c.cutout((slice(2, 4), slice(3, 5), slice(4, 8)))
+    assert sub.shape == (2, 2, 4) and tuple(sub.voxel_offset) == (2, 3, 4) and sub.array[0, 0, 0] == c.array[1, 1, 1]
+    with pytest.raises(IndexError):
+        c.cutout((slice(0, 2), slice(3, 5), slice(4, 8)))
+    out = Chunk(np.ones((3, 4, 5, 6), np.float32), voxel_offset=(1, 2, 3), voxel_size=(40, 4, 4))
+    out *= Chunk(np.full((4, 5, 6), 0.5, np.float32), voxel_offset=(1, 2, 3))
+    assert isinstance(out, Chunk) and tuple(out.voxel_size) == (40, 4, 4) and np.all(out.array == 0.5)
+    aff = Chunk(np.stack([np.ones((2, 2, 2), np.float32)] * 3 + [np.array([[[0.1, 0.5]] * 2] * 2, np.float32)]))
+    masked = aff.mask_using_last_channel(threshold=0.3)
+    assert masked.shape == (3, 2, 2, 2) and np.array_equal(masked.array[0, 0, 0], [1, 0])
+
+
+def test_chunk_create_sin_matches_reference_formula():
+    c = Chunk.create(size=(6, 10, 12), dtype=np.uint8, pattern="sin")
+    iz, iy, ix = np.meshgrid(*[np.linspace(0, 1, n) for n in (6, 10, 12)], indexing="ij")
+    assert np.array_equal(c.array, (np.abs(np.sin(4 * (iz + iy + ix))) * 255).astype(np.uint8))
+    assert c.layer_type == "image"
+
+
+def test_native_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "chunkflow_b200.h")).read()
+    declared = set(re.findall(r"\b(cfb_[a-z0-9_]+)\s*\(", header)) - {"cfb_engine"}
+    lib = _native.load()
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in include/chunkflow_b200.h but not exported"
+    assert declared == set(_native.EXPORTS)
+    assert lib.cfb_version() >= 100
+
+
+@pytest.mark.parametrize("ps,ov", [((20, 256, 256), (4, 64, 64)), ((32, 256, 256), (8, 64, 64)), ((8, 32, 32), (2, 8, 8))])
+def test_native_patch_mask_is_bit_identical_to_reference(geometry, ps, ov):
+    m = _native.make_patch_mask(ps, ov)
+    g = geometry["patch_masks"]["x".join(map(str, ps)) + "_" + "x".join(map(str, ov))]
+    assert hashlib.sha256(m.tobytes()).hexdigest() == g["sha256"]
+
+
+def test_patch_mask_partition_of_unity():
+    ps, ov = (8, 32, 32), (2, 8, 8)
+    m = _native.make_patch_mask(ps, ov).astype(np.float64)
+    st = tuple(p - o for p, o in zip(ps, ov))
+    acc = np.zeros(tuple(p + 2 * s for p, s in zip(ps, st)))
+    for a in range(3):
+        for b in range(3):
+            for c in range(3):
+                acc[a * st[0]:a * st[0] + ps[0], b * st[1]:b * st[1] + ps[1], c * st[2]:c * st[2] + ps[2]] += m
+    centre = acc[st[0]:st[0] + ps[0], st[1]:st[1] + ps[1], st[2]:st[2] + ps[2]]
+    np.testing.assert_allclose(centre, 1.0, atol=1e-6)
+
+
+def test_product_tta_matches_oracle_for_spatial_transposes():
+    from chunkflow_b200.flow.divid_conquer.transform import TransformSequences
+    rng = np.random.default_rng(3)
+    a = rng.random((1, 1, 3, 8, 8)).astype(np.float32)
+    ts = TransformSequences()
+    fw = ts.forward(a)
+    assert len(fw) == 8 and all(np.array_equal(x, y) for x, y in zip(ts.backward(fw), [a] * 8))
+    # distinct spatial variants (the reference's flips act on batch/channel axes instead)
+    assert len({x.tobytes() for x in fw}) == 8
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_a_gpu():
+    from chunkflow_b200 import Inferencer
+    with pytest.raises(_native.NativeError) as ei:
+        Inferencer(None, None, (8, 32, 32), output_patch_overlap=(2, 8, 8), framework="identity")
+    assert ei.value.code == _native.ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "chunkflow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"

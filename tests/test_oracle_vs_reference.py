@@ -1,0 +1,80 @@
+"""Pins the oracle to the REAL reference classes (only where /root/reference exists).
+Ports of the reference's own hot-path tests, tests/flow/divid_conquer/test_inferencer.py."""
+import io
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+from oracle import inferencer_oracle as O
+from oracle import reference_harness as H
+
+pytestmark = pytest.mark.skipif(not H.available(), reason="/root/reference not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import torch
+    torch.cuda.is_available = lambda: False
+    return H.import_reference()
+
+
+def _run_ref(ref, chunk, offset=(0, 0, 0), **kw):
+    Inferencer, Chunk, _ = ref
+    with redirect_stdout(io.StringIO()):
+        with Inferencer(kw.pop("model", None), None, kw.pop("input_patch_size"), **kw) as inf:
+            out = inf(Chunk(chunk, voxel_offset=offset))
+    return out
+
+
+def test_non_aligned_input_chunk(ref):  # reference test_inferencer.py:141-169 (smaller in z)
+    rng = np.random.default_rng(1)
+    img = rng.integers(1, 255, size=(28 + 4 + 6, 192 + 64 + 7, 192 * 2 + 64 + 9), dtype=np.uint8)
+    r = _run_ref(ref, img, input_patch_size=(32, 256, 256), output_patch_overlap=(4, 64, 64), num_output_channels=2,
+                 batch_size=5, framework="identity", mask_output_chunk=True)
+    o, _ = O.infer_chunk(img, input_patch_size=(32, 256, 256), output_patch_overlap=(4, 64, 64), num_output_channels=2,
+                         framework="identity")
+    assert np.array_equal(r.array, o)
+    np.testing.assert_allclose(img.astype(np.float32) / 255, o[0], rtol=1e-5, atol=1e-5)
+
+
+def test_aligned_input_size_and_offset(ref):  # reference test_inferencer.py:34-58
+    Inferencer, Chunk, _ = ref
+    with redirect_stdout(io.StringIO()):
+        image = Chunk.create(size=(18, 224, 224), dtype="uint8")
+    r = _run_ref(ref, image.array, offset=(5, 6, 7), input_patch_size=(10, 128, 128), num_output_channels=3,
+                 output_patch_overlap=(2, 32, 32), input_size=(18, 224, 224), mask_output_chunk=False,
+                 framework="identity", dtype="float32")
+    o, off = O.infer_chunk(image.array, (5, 6, 7), input_patch_size=(10, 128, 128), output_patch_overlap=(2, 32, 32),
+                           num_output_channels=3, framework="identity", mask_output_chunk=False)
+    assert tuple(r.voxel_offset) == off == (7, 38, 39)
+    assert np.array_equal(r.array, o)
+
+
+def test_test_time_augmentation(ref):  # reference test_inferencer.py:6-32
+    Inferencer, Chunk, _ = ref
+    with redirect_stdout(io.StringIO()):
+        image = Chunk.create(size=(18, 224, 224), dtype="uint8")
+    r = _run_ref(ref, image.array, input_patch_size=(10, 128, 128), num_output_channels=3,
+                 output_patch_overlap=(2, 32, 32), input_size=(18, 224, 224), mask_output_chunk=False,
+                 framework="identity", augment=True, dtype="float32")
+    o, _ = O.infer_chunk(image.array, input_patch_size=(10, 128, 128), output_patch_overlap=(2, 32, 32),
+                         num_output_channels=3, framework="identity", mask_output_chunk=False, augment=True)
+    np.testing.assert_allclose(r.array, o, rtol=0, atol=1e-7)
+
+
+def test_network_path_bit_exact(ref, unet_model):
+    from conftest import MODEL_FILE
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, size=(10, 36, 44), dtype=np.uint8)
+    r = _run_ref(ref, img, model=MODEL_FILE, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8),
+                 num_output_channels=3, batch_size=1, framework="pytorch", mask_output_chunk=True)
+    o, _ = O.infer_chunk(img, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3,
+                         framework="pytorch", model=unet_model)
+    assert np.array_equal(r.array, o)
+
+
+def test_myelin_and_patch_mask(ref):
+    _, _, PatchMask = ref
+    for ps, ov in [((10, 128, 128), (2, 32, 32)), ((8, 32, 32), (2, 8, 8))]:
+        assert np.array_equal(np.asarray(PatchMask(ps, ov)), O.make_patch_mask(ps, ov))

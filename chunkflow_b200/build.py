@@ -40,7 +40,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libchunkflow_b200.so")
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *sources(), "-lcuda", "-o", LIB_PATH]
+    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *sources(), "-o", LIB_PATH]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

@@ -1,0 +1,472 @@
+// tcgen05 / TMA implicit-GEMM 3x3x3 convolution for sm_100a.  See kernels_umma.cuh for the
+// activation layout.  One CTA owns a (batch, y-tile, x-tile) column of the patch and marches
+// along z with a ring of three z-planes in shared memory:
+//
+//   warp 0   : A producer  -- one TMA box per z-plane (halo rows/cols, zero fill outside the patch)
+//   warp 1   : B producer  -- packed weight blocks per (tap, K-group) via cp.async.bulk
+//   warp 2   : MMA issuer  -- per z-plane job: 27 taps x K-steps x G tiles of tcgen05.mma
+//                             (M=128 voxels, N=Cout or 2*Cout, K=16) accumulating in TMEM
+//   warps 3-6: epilogue    -- tcgen05.ld, bias+ReLU, fp16 (hi/lo) pack, coalesced 16-byte stores
+//
+// Precision: fp16 operands, fp32 accumulation.  In split mode every value is hi+lo
+// (two fp16, ~22 bits): MMA1 = a_hi x [w_hi | w_lo] (N = 2*Cout, one pass over A) and
+// MMA2 = a_lo x w_hi (N = Cout); the epilogue adds the two accumulator halves.
+#include "kernels_umma.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <vector>
+
+#include "chunkflow_b200.h"
+
+namespace cfb {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a launch failure (trap) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz
+      printf("chunkflow_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address, leading byte offset (between the two 8-element K chunks) and stride byte
+// offset (between 8-row groups), all in 16-byte units; bits [46,48) = 1 (Blackwell version).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)(addr16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) |
+         (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct UmmaConvParams {
+  int Z, Y, X;
+  int XT, TY, pitch, tile_stride, G;
+  int tiles_x, tiles_y;
+  int planes_a, planes_b;  // 8-channel chunks of source A / source B
+  uint32_t plane_stride;   // bytes of one (TY+2) x pitch x 16 B plane in smem
+  uint32_t slot_stride;    // bytes of one z-plane slot (all chunk/part planes)
+  const __half* wpacked;
+  const float* bias;
+  __half* out;
+  int relu;
+};
+
+constexpr int kRing = 3;       // z-plane ring slots
+constexpr int kBStages = 4;    // weight block stages
+constexpr int kThreads = 224;  // 7 warps
+constexpr int kTailPad = 2304; // dense M tiles may read up to 129 voxel records past the last plane
+constexpr int kBufCols = 256;  // TMEM columns per accumulator buffer (2 buffers)
+
+template <int CIN, int COUT, bool SPLIT>
+struct ConvCfg {
+  static constexpr int P = SPLIT ? 2 : 1;
+  static constexpr int NPL = P * CIN / 8;            // planes per slot
+  static constexpr int NB = P * COUT;                // rows of a weight block = N of MMA1
+  static constexpr int KB = CIN >= 32 ? 32 : 16;     // channels per weight block
+  static constexpr int KG = CIN / KB;                // weight blocks per tap
+  static constexpr int KS = KB / 16;                 // K=16 steps per weight block
+  static constexpr int BSTAGE = NB * KB * 2;         // bytes
+  static constexpr int MAXG = kBufCols / NB;
+};
+
+template <int CIN, int COUT, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const UmmaConvParams p) {
+  using Cfg = ConvCfg<CIN, COUT, SPLIT>;
+  constexpr int P = Cfg::P;
+  extern __shared__ uint8_t smem_raw[];
+  // TMA destinations need 128-byte alignment; the launch reserves 128 spare bytes for this
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = blockIdx.x % p.tiles_x;
+  const int ty = (blockIdx.x / p.tiles_x) % p.tiles_y;
+  const int b = blockIdx.x / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.XT, y0 = ty * p.TY;
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kRing * p.slot_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kBStages * Cfg::BSTAGE);
+  // barrier map: [0..2] a_full, [3..5] a_empty, [6..9] b_full, [10..13] b_empty, [14,15] acc_full, [16,17] acc_empty
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(10 + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(14 + i), 1); mbar_init(BAR(16 + i), 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int Z = p.Z;
+  if (warp == 0) {
+    // ---------------- A producer: z-planes -1 .. Z into the ring ----------------
+    if (lane == 0) {
+      const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
+      const int plane_a0 = b * p.planes_a * P, plane_b0 = b * p.planes_b * P;
+      for (int q = 0; q < Z + 2; ++q) {
+        const int slot = q % kRing;
+        if (q >= kRing) mbar_wait(BAR(3 + slot), ((q / kRing) - 1) & 1);
+        mbar_expect_tx(BAR(slot), tx_bytes);
+        const uint32_t dst = smem_u32(sA + (size_t)slot * p.slot_stride);
+        tma_load_5d(dst, &mapA, BAR(slot), 0, x0 - 1, y0 - 1, q - 1, plane_a0);
+        if (p.planes_b > 0)
+          tma_load_5d(dst + (uint32_t)(p.planes_a * P) * p.plane_stride, &mapB, BAR(slot), 0, x0 - 1, y0 - 1, q - 1,
+                      plane_b0);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- B producer: weight blocks, 27 * KG per z-plane job ----------------
+    if (lane == 0) {
+      const uint32_t total = (uint32_t)Z * 27u * Cfg::KG;
+      const uint32_t per_job = 27u * Cfg::KG;
+      for (uint32_t i = 0; i < total; ++i) {
+        const uint32_t st = i % kBStages;
+        if (i >= kBStages) mbar_wait(BAR(10 + st), ((i / kBStages) - 1) & 1);
+        mbar_expect_tx(BAR(6 + st), Cfg::BSTAGE);
+        bulk_load(smem_u32(sB + st * Cfg::BSTAGE),
+                  reinterpret_cast<const uint8_t*>(p.wpacked) + (size_t)(i % per_job) * Cfg::BSTAGE, Cfg::BSTAGE,
+                  BAR(6 + st));
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t IDESC1 = make_idesc(Cfg::NB);
+      constexpr uint32_t IDESC2 = make_idesc(COUT);
+      const uint32_t plane16 = p.plane_stride >> 4;
+      const uint32_t sA16 = smem_u32(sA) >> 4, slot16 = p.slot_stride >> 4;
+      const uint32_t sB16 = smem_u32(sB) >> 4;
+      uint32_t bi = 0;
+      for (int z = 0; z < Z; ++z) {
+        const int buf = z & 1;
+        if (z >= 2) mbar_wait(BAR(16 + buf), ((z >> 1) - 1) & 1);
+        tc_fence_after();
+        for (int dz = 0; dz < 3; ++dz) {
+          const int q = z + dz, slot = q % kRing;
+          mbar_wait(BAR(slot), (q / kRing) & 1);
+          tc_fence_after();
+          const uint32_t a_slot16 = sA16 + slot * slot16;
+          for (int t9 = 0; t9 < 9; ++t9) {
+            const uint32_t tapoff = (uint32_t)((t9 / 3) * p.pitch + (t9 % 3));
+            for (int kg = 0; kg < Cfg::KG; ++kg, ++bi) {
+              const uint32_t st = bi % kBStages;
+              mbar_wait(BAR(6 + st), (bi / kBStages) & 1);
+              tc_fence_after();
+              const uint32_t b16 = sB16 + st * (Cfg::BSTAGE >> 4);
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KS; ++ks) {
+                const uint32_t chunk0 = (uint32_t)(kg * Cfg::KS + ks) * 2u;
+                const uint64_t bdesc = make_desc(b16 + (uint32_t)ks * 2u * Cfg::NB, Cfg::NB, 8);
+                const uint32_t a_k16 = a_slot16 + chunk0 * P * plane16 + tapoff;
+                const uint32_t first = (dz == 0 && t9 == 0 && kg == 0 && ks == 0) ? 0u : 1u;
+                for (int g = 0; g < p.G; ++g) {
+                  const uint32_t a16 = a_k16 + (uint32_t)(g * p.tile_stride);
+                  const uint32_t d = tmem_base + (uint32_t)(buf * kBufCols + g * Cfg::NB);
+                  tc_mma_f16(d, make_desc(a16, P * plane16, 8), bdesc, IDESC1, first);
+                  if (SPLIT) tc_mma_f16(d, make_desc(a16 + plane16, P * plane16, 8), bdesc, IDESC2, 1u);
+                }
+              }
+              tc_commit(BAR(10 + st));  // weight block consumed
+            }
+          }
+          if (dz == 0) tc_commit(BAR(3 + slot));  // plane z-1 is dead: the producer may refill its slot
+        }
+        tc_commit(BAR(14 + buf));  // accumulators of this z-plane are complete
+      }
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> bias/ReLU -> fp16 (hi/lo) -> HBM ----------------
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
+    const size_t plane_vox = (size_t)p.Z * p.Y * p.X;
+    uint4* out16 = reinterpret_cast<uint4*>(p.out);
+    for (int z = 0; z < Z; ++z) {
+      const int buf = z & 1;
+      mbar_wait(BAR(14 + buf), (z >> 1) & 1);
+      tc_fence_after();
+      for (int g = 0; g < p.G; ++g) {
+        const int m = wq * 32 + lane;
+        const int qpos = g * p.tile_stride + m;
+        const int row = qpos / p.pitch, col = qpos - row * p.pitch;
+        const bool valid = row < ty_valid && col < xt_valid;
+        const size_t vox = ((size_t)z * p.Y + (y0 + row)) * p.X + (x0 + col);
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kBufCols + g * Cfg::NB);
+#pragma unroll
+        for (int cb = 0; cb < COUT / 16; ++cb) {
+          uint32_t r[16];
+          tc_ld16(taddr + cb * 16, r);
+          float v[16];
+          if (SPLIT) {
+            uint32_t r2[16];
+            tc_ld16(taddr + COUT + cb * 16, r2);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+          } else {
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            v[i] += __ldg(p.bias + cb * 16 + i);
+            if (p.relu) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (valid) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int chunk = cb * 2 + h;
+              float hi[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
+              const size_t plane = ((size_t)b * (COUT / 8) + chunk) * P;
+              out16[plane * plane_vox + vox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
+                                                          pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+              if (SPLIT) {
+                float lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
+                out16[(plane + 1) * plane_vox + vox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
+                                                                  pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(16 + buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side: tensor maps, tile selection, launch
+// ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CFB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !ptr) throw std::runtime_error("cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// CP8 tensor (planes, Z, Y, X, 8) fp16 -> 5-D tensor map with box (8, bx, by, 1, bplanes)
+CUtensorMap make_map(const __half* base, int planes, Int3 sz, int bx, int by, int bplanes) {
+  CUtensorMap m;
+  cuuint64_t gdim[5] = {8, (cuuint64_t)sz.x, (cuuint64_t)sz.y, (cuuint64_t)sz.z, (cuuint64_t)planes};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)sz.x * 16, (cuuint64_t)sz.x * sz.y * 16, (cuuint64_t)sz.x * sz.y * sz.z * 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)bplanes};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return m;
+}
+
+constexpr int kMaxSmem = 232448;  // 227 KB
+
+template <int CIN, int COUT, bool SPLIT>
+void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
+                Int3 sz, bool relu, cudaStream_t s) {
+  using Cfg = ConvCfg<CIN, COUT, SPLIT>;
+  UmmaConvParams p{};
+  p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
+  p.XT = std::min(sz.x, 128);
+  p.pitch = p.XT + 2 + (p.XT & 1);
+  const bool row_aligned = p.XT == 128;
+  p.tile_stride = row_aligned ? p.pitch : 128;
+  p.tiles_x = ceil_div(sz.x, p.XT);
+  const int fixed = kBStages * Cfg::BSTAGE + 256 + kTailPad + 128;
+  int best_ty = 0;
+  const int ty_cap = std::min(16, (sz.y + 1) & ~1);
+  for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
+    const size_t plane = (size_t)(tyc + 2) * p.pitch * 16;
+    const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
+    const int G = row_aligned ? tyc : ceil_div(tyc * p.pitch, 128);
+    if ((size_t)kRing * slot + fixed <= (size_t)kMaxSmem && G <= Cfg::MAXG && tyc + 2 <= 256 && slot < (1u << 18)) {
+      best_ty = tyc;
+      break;
+    }
+  }
+  if (!best_ty) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
+  p.TY = best_ty;
+  p.G = row_aligned ? p.TY : ceil_div(p.TY * p.pitch, 128);
+  p.tiles_y = ceil_div(sz.y, p.TY);
+  p.plane_stride = (uint32_t)((p.TY + 2) * p.pitch * 16);
+  p.slot_stride = (uint32_t)((Cfg::NPL * (size_t)p.plane_stride + 127) / 128 * 128);
+  p.planes_a = ca / 8; p.planes_b = cb / 8;
+  p.wpacked = w.w; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
+  const size_t smem = (size_t)kRing * p.slot_stride + fixed;
+  const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P);
+  const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P) : mapA;
+  auto kern = conv3_umma_kernel<CIN, COUT, SPLIT>;
+  CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, mapB, p);
+  CFB_LAUNCH_CHECK();
+}
+
+template <bool SPLIT>
+void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb, Int3 sz,
+              bool relu, cudaStream_t s) {
+  const int cin = ca + cb, cout = w.cout;
+#define CFB_CASE(CI, CO) \
+  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+  CFB_CASE(16, 16) CFB_CASE(16, 32) CFB_CASE(32, 32) CFB_CASE(32, 64) CFB_CASE(64, 64) CFB_CASE(64, 32) CFB_CASE(32, 16)
+#undef CFB_CASE
+  throw std::runtime_error("conv3_umma: unsupported channel configuration " + std::to_string(cin) + "->" + std::to_string(cout));
+}
+
+}  // namespace
+
+void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
+                       Int3 sz, bool relu, cudaStream_t s) {
+  if (ca % 16 || (cb % 16) || w.cin != ca + cb) throw std::runtime_error("conv3_umma: channel mismatch");
+  if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+  else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight packing (host)
+// ------------------------------------------------------------------------------------------
+void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out) {
+  free_packed(out);
+  const int KB = cin >= 32 ? 32 : 16, KG = cin / KB, NB = parts * cout;
+  const size_t block = (size_t)NB * KB;  // halves
+  std::vector<__half> buf((size_t)27 * KG * block);
+  for (int t = 0; t < 27; ++t)
+    for (int g = 0; g < KG; ++g)
+      for (int kc = 0; kc < KB / 8; ++kc)
+        for (int n = 0; n < NB; ++n)
+          for (int e = 0; e < 8; ++e) {
+            const int ci = g * KB + kc * 8 + e;
+            const int co = n % cout;
+            const float wv = h_w[((size_t)co * cin + ci) * 27 + t];
+            const __half hi = __float2half_rn(wv);
+            const __half val = n < cout ? hi : __float2half_rn(wv - __half2float(hi));
+            buf[((size_t)t * KG + g) * block + ((size_t)kc * NB + n) * 8 + e] = val;
+          }
+  out.cin = cin; out.cout = cout; out.parts = parts;
+  out.bytes = buf.size() * sizeof(__half);
+  CFB_CUDA(cudaMalloc(&out.w, out.bytes));
+  CFB_CUDA(cudaMemcpy(out.w, buf.data(), out.bytes, cudaMemcpyHostToDevice));
+  CFB_CUDA(cudaMalloc(&out.bias, cout * sizeof(float)));
+  CFB_CUDA(cudaMemcpy(out.bias, h_bias, cout * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void free_packed(PackedConv& p) {
+  if (p.w) cudaFree(p.w);
+  if (p.bias) cudaFree(p.bias);
+  p = PackedConv{};
+}
+
+}  // namespace cfb

@@ -1,0 +1,57 @@
+// tcgen05 / TMA implicit-GEMM 3x3x3 convolution and the fp16 "chunk-planar" activation
+// layout it works on.  Declarations.
+//
+// Activation layout in HBM ("CP8"): (batch, C/8, P, Z, Y, X, 8) fp16, where P = 1 (single
+// fp16) or 2 (hi/lo split: value = hi + lo, |lo| <= ulp(hi)/2, ~22 significant bits).  One
+// (chunk, part) plane is a dense (Z, Y, X, 8) array of 16-byte voxel records, so that
+//   * TMA can stage a halo box of any (z, y, x) offset into shared memory with zero fill
+//     outside the patch (SAME padding at the PATCH border for free), and
+//   * the staged box IS the canonical no-swizzle K-major UMMA operand layout: 8 consecutive
+//     voxels x 16 bytes form one core matrix, a tap shift of the 3x3x3 stencil is a plain
+//     +16 B x (dy*pitch + dx) on the descriptor start address, and the second 8-channel chunk
+//     of a K=16 step sits one plane further (leading byte offset).
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace cfb {
+
+// Weights of one 3x3x3 layer packed for the B operand: for tap t (27), K-group g:
+// [KB/8][NB rows][8] fp16, rows 0..COUT-1 = fp16(w), rows COUT..2COUT-1 = fp16(w - fp16(w)) (split only).
+struct PackedConv {
+  __half* w = nullptr;  // device
+  float* bias = nullptr;
+  int cin = 0, cout = 0, parts = 1;
+  size_t bytes = 0;
+};
+
+void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out);
+void free_packed(PackedConv& p);
+
+// One 3x3x3 convolution + bias + ReLU on tcgen05.  Input = channel concat of srcA (ca channels)
+// and srcB (cb channels, may be null); all tensors CP8 with `parts` parts.
+void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out,
+                       int nb, Int3 size, bool relu, cudaStream_t s);
+
+// Layout conversion (tests / debug): planar fp32 (nb, C, Z,Y,X) <-> CP8.
+void launch_planar_to_cp8(const float* in, __half* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
+void launch_cp8_to_planar(const __half* in, float* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
+
+// First layer: extract `nb` patches from the uint8/f32 chunk (normalised by 1/255), 3x3x3
+// convolution 1 -> 16 in fp32 on CUDA cores, ReLU, CP8 output.  w: (16,1,3,3,3) fp32.
+void launch_first_conv_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb,
+                           Int3 patch, const float* w, const float* bias, __half* out, int parts, cudaStream_t s);
+// Same from already extracted fp32 patches (nb,1,Z,Y,X) (plugin level / debug).
+void launch_first_conv_cp8_from_patches(const float* patches, int nb, Int3 patch, const float* w, const float* bias,
+                                        __half* out, int parts, cudaStream_t s);
+
+void launch_maxpool_cp8(const __half* in, __half* out, int channels, int parts, int nb, Int3 in_size, cudaStream_t s);
+// ConvTranspose kernel=stride=(1,2,2), fp32 math on CUDA cores.  w: (cin, cout, 1,2,2) fp32.
+void launch_convT_cp8(const __half* in, const float* w, const float* bias, __half* out, int cin, int cout,
+                      int parts, int nb, Int3 in_size, cudaStream_t s);
+// 1x1x1 head + sigmoid -> planar fp32 (nb, cout, Z,Y,X).
+void launch_head_sigmoid_cp8(const __half* in, const float* w, const float* bias, float* out, int cin, int cout,
+                             int parts, int nb, Int3 size, cudaStream_t s);
+
+}  // namespace cfb

@@ -24,8 +24,6 @@ const Spec kSpecs[] = {
 void Network::configure(int precision, Int3 patch, int batch) {
   if (precision != CFB_PRECISION_F32_SIMT && precision != CFB_PRECISION_F16X3_UMMA && precision != CFB_PRECISION_F16_UMMA)
     throw std::invalid_argument("unknown precision mode");
-  if (precision != CFB_PRECISION_F32_SIMT)
-    throw std::runtime_error("tcgen05 precision modes are not built into this library yet");
   precision_ = precision;
   patch_ = patch;
   batch_ = batch;
@@ -34,7 +32,7 @@ void Network::configure(int precision, Int3 patch, int batch) {
 void Network::release() {
   for (void* p : owned_) cudaFree(p);
   owned_.clear();
-  for (auto& kv : layers_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+  for (auto& kv : layers_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); free_packed(kv.second.packed); }
   layers_.clear();
   for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
   prof_pool_.clear();
@@ -62,17 +60,33 @@ void Network::allocate() {
     return p;
   };
   patch_input_buffer(1);
+  net_out_ = alloc((int64_t)std::max(cnet_, 1) * v0);
+  if (umma()) {
+    const int P = parts();
+    auto halloc = [&](int64_t channels, int64_t v) {
+      __half* p = nullptr;
+      CFB_CUDA(cudaMalloc(&p, (size_t)channels * P * v * batch_ * sizeof(__half)));
+      owned_.push_back(p);
+      return p;
+    };
+    h_e0a_ = halloc(16, v0); h_e0_ = halloc(16, v0); h_p0_ = halloc(16, v1);
+    h_e1a_ = halloc(32, v1); h_e1_ = halloc(32, v1); h_p1_ = halloc(32, v2);
+    h_e2a_ = halloc(64, v2); h_e2_ = halloc(64, v2);
+    h_u1_ = halloc(32, v1); h_d1a_ = halloc(32, v1); h_d1_ = halloc(32, v1);
+    h_u0_ = halloc(16, v0); h_d0a_ = halloc(16, v0); h_d0_ = halloc(16, v0);
+    e0a_ = net_out_;  // marks "allocated"
+    return;
+  }
   e0a_ = alloc(16 * v0); e0_ = alloc(16 * v0); p0_ = alloc(16 * v1);
   e1a_ = alloc(32 * v1); e1_ = alloc(32 * v1); p1_ = alloc(32 * v2);
   e2a_ = alloc(64 * v2); e2_ = alloc(64 * v2);
   u1_ = alloc(32 * v1); d1a_ = alloc(32 * v1); d1_ = alloc(32 * v1);
   u0_ = alloc(16 * v0); d0a_ = alloc(16 * v0); d0_ = alloc(16 * v0);
-  net_out_ = alloc((int64_t)std::max(cnet_, 1) * v0);
 }
 
 bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int num_output_channels, std::string& err) {
   ready_ = false;
-  for (auto& kv : layers_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); }
+  for (auto& kv : layers_) { cudaFree(kv.second.w); cudaFree(kv.second.bias); free_packed(kv.second.packed); }
   layers_.clear();
   for (const Spec& sp : kSpecs) {
     const std::string wn = std::string(sp.name) + ".weight", bn = std::string(sp.name) + ".bias";
@@ -92,6 +106,8 @@ bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int 
     CFB_CUDA(cudaMalloc(&L.bias, bi->second.size() * sizeof(float)));
     CFB_CUDA(cudaMemcpy(L.w, wi->second.data(), wi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
     CFB_CUDA(cudaMemcpy(L.bias, bi->second.data(), bi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (umma() && sp.taps == 27 && sp.cin >= 16)
+      pack_conv3_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
     layers_[sp.name] = L;
   }
   if (num_output_channels > cnet_) { err = "the network produces fewer channels than num_output_channels"; return false; }
@@ -170,8 +186,42 @@ int Network::forward(int nb, cudaStream_t s) {
   return 15;
 }
 
+int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s) {
+  const Int3 s0 = patch_, s1{patch_.z, patch_.y / 2, patch_.x / 2}, s2{patch_.z, patch_.y / 4, patch_.x / 4};
+  const int P = parts();
+  {
+    const ConvLayer& L = layers_.at("enc0.0");
+    prof_begin("enc0.0", s);
+    if (chunk) launch_first_conv_cp8(chunk, in_dtype, cs, patches, nb, s0, L.w, L.bias, h_e0a_, P, s);
+    else launch_first_conv_cp8_from_patches(buf_in_, nb, s0, L.w, L.bias, h_e0a_, P, s);
+    prof_end(s);
+  }
+  auto conv = [&](const char* name, const __half* a, int ca, const __half* b, int cb, __half* out, Int3 sz) {
+    const ConvLayer& L = layers_.at(name);
+    prof_begin(name, s);
+    launch_conv3_umma(a, ca, b, cb, L.packed, out, nb, sz, /*relu=*/true, s);
+    prof_end(s);
+  };
+  conv("enc0.2", h_e0a_, 16, nullptr, 0, h_e0_, s0);
+  prof_begin("pool0", s); launch_maxpool_cp8(h_e0_, h_p0_, 16, P, nb, s0, s); prof_end(s);
+  conv("enc1.0", h_p0_, 16, nullptr, 0, h_e1a_, s1);
+  conv("enc1.2", h_e1a_, 32, nullptr, 0, h_e1_, s1);
+  prof_begin("pool1", s); launch_maxpool_cp8(h_e1_, h_p1_, 32, P, nb, s1, s); prof_end(s);
+  conv("enc2.0", h_p1_, 32, nullptr, 0, h_e2a_, s2);
+  conv("enc2.2", h_e2a_, 64, nullptr, 0, h_e2_, s2);
+  { const ConvLayer& L = layers_.at("up1"); prof_begin("up1", s); launch_convT_cp8(h_e2_, L.w, L.bias, h_u1_, 64, 32, P, nb, s2, s); prof_end(s); }
+  conv("dec1.0", h_u1_, 32, h_e1_, 32, h_d1a_, s1);  // torch.cat([up1, enc1])
+  conv("dec1.2", h_d1a_, 32, nullptr, 0, h_d1_, s1);
+  { const ConvLayer& L = layers_.at("up0"); prof_begin("up0", s); launch_convT_cp8(h_d1_, L.w, L.bias, h_u0_, 32, 16, P, nb, s1, s); prof_end(s); }
+  conv("dec0.0", h_u0_, 16, h_e0_, 16, h_d0a_, s0);  // torch.cat([up0, enc0])
+  conv("dec0.2", h_d0a_, 16, nullptr, 0, h_d0_, s0);
+  { const ConvLayer& L = layers_.at("head"); prof_begin("head", s); launch_head_sigmoid_cp8(h_d0_, L.w, L.bias, net_out_, 16, cnet_, P, nb, s0, s); prof_end(s); }
+  return 15;
+}
+
 int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s) {
   if (nb > batch_) throw std::invalid_argument("batch larger than configured");
+  if (umma()) return forward_cp8(chunk, in_dtype, cs, patches, nb, s);
   prof_begin("extract", s);
   launch_extract_patches(chunk, in_dtype, cs, patches, nb, patch_, buf_in_, s);
   prof_end(s);
@@ -181,6 +231,7 @@ int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const 
 int Network::forward_from_host_patches(const float* h_patches, int nb, cudaStream_t s) {
   if (nb > batch_) throw std::invalid_argument("batch larger than configured");
   CFB_CUDA(cudaMemcpyAsync(buf_in_, h_patches, (size_t)nb * vol(patch_) * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (umma()) return forward_cp8(nullptr, 0, Int3{0, 0, 0}, nullptr, nb, s);
   return forward(nb, s);
 }
 
@@ -211,6 +262,26 @@ int Network::debug_conv3(const float* h_in, int cin, Int3 size, const float* h_w
   CFB_CUDA(cudaMemcpyAsync(d_in, h_in, (size_t)cin * v * 4, cudaMemcpyHostToDevice, s));
   CFB_CUDA(cudaMemcpyAsync(d_w, h_w, (size_t)cout * cin * 27 * 4, cudaMemcpyHostToDevice, s));
   CFB_CUDA(cudaMemcpyAsync(d_b, h_b, (size_t)cout * 4, cudaMemcpyHostToDevice, s));
+  if (umma()) {
+    if (cin % 16) { cudaFree(d_in); cudaFree(d_w); cudaFree(d_b); cudaFree(d_out); throw std::runtime_error("tcgen05 conv needs cin % 16 == 0"); }
+    const int P = parts();
+    __half *c_in = nullptr, *c_out = nullptr;
+    CFB_CUDA(cudaMalloc(&c_in, (size_t)cin * P * v * 2));
+    CFB_CUDA(cudaMalloc(&c_out, (size_t)cout * P * v * 2));
+    PackedConv pk;
+    pack_conv3_weights(h_w, h_b, cin, cout, P, pk);
+    launch_planar_to_cp8(d_in, c_in, cin, P, 1, size, s);
+    // exercise the two-source (concat) path whenever the channel count allows it
+    const int ca = cin >= 32 ? cin / 2 : cin, cb = cin - ca;
+    launch_conv3_umma(c_in, ca, cb ? c_in + (size_t)ca * P * v : nullptr, cb, pk, c_out, 1, size, relu, s);
+    launch_cp8_to_planar(c_out, d_out, cout, P, 1, size, s);
+    CFB_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)cout * v * 4, cudaMemcpyDeviceToHost, s));
+    cudaError_t err = cudaStreamSynchronize(s);
+    cudaFree(c_in); cudaFree(c_out); free_packed(pk);
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_b); cudaFree(d_out);
+    CFB_CUDA(err);
+    return CFB_OK;
+  }
   launch_conv3_f32(d_in, cin, nullptr, 0, d_w, d_b, d_out, cout, 1, size, relu, s);
   CFB_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)cout * v * 4, cudaMemcpyDeviceToHost, s));
   CFB_CUDA(cudaStreamSynchronize(s));

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels_umma.cuh"
 
 namespace cfb {
 
@@ -15,6 +16,7 @@ struct ConvLayer {
   int cin = 0, cout = 0;
   float* w = nullptr;     // fp32, state_dict layout
   float* bias = nullptr;  // fp32
+  PackedConv packed;      // fp16 (hi/lo) B-operand blocks for the tcgen05 path (3x3x3 layers, cin >= 16)
 };
 
 class Network {
@@ -44,7 +46,11 @@ class Network {
 
  private:
   void allocate();
-  int forward(int nb, cudaStream_t s);  // from buf_in_
+  int forward(int nb, cudaStream_t s);  // from buf_in_ (fp32 SIMT path)
+  // tcgen05 path: chunk != nullptr -> first layer reads the chunk, else the staged fp32 patches in buf_in_
+  int forward_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, cudaStream_t s);
+  bool umma() const { return precision_ != 0; }
+  int parts() const { return precision_ == 1 ? 2 : 1; }
 
   struct Span { int id; cudaEvent_t a, b; };
   void prof_begin(const char* name, cudaStream_t s);
@@ -68,6 +74,10 @@ class Network {
   float *buf_in_ = nullptr, *e0a_ = nullptr, *e0_ = nullptr, *p0_ = nullptr, *e1a_ = nullptr, *e1_ = nullptr,
         *p1_ = nullptr, *e2a_ = nullptr, *e2_ = nullptr, *u1_ = nullptr, *d1a_ = nullptr, *d1_ = nullptr,
         *u0_ = nullptr, *d0a_ = nullptr, *d0_ = nullptr, *net_out_ = nullptr;
+  // CP8 fp16 activations of the tcgen05 path
+  __half *h_e0a_ = nullptr, *h_e0_ = nullptr, *h_p0_ = nullptr, *h_e1a_ = nullptr, *h_e1_ = nullptr, *h_p1_ = nullptr,
+         *h_e2a_ = nullptr, *h_e2_ = nullptr, *h_u1_ = nullptr, *h_d1a_ = nullptr, *h_d1_ = nullptr, *h_u0_ = nullptr,
+         *h_d0a_ = nullptr, *h_d0_ = nullptr;
 };
 
 }  // namespace cfb

@@ -273,7 +273,7 @@ def main():
         print(json.dumps({
             "metric": "Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if eng.params.precision == 0 else "f16", "precision_mode": precision,
+            "vs_baseline": None, "dtype": {0: "f32", 1: "f16x3", 2: "f16"}[eng.params.precision], "precision_mode": precision,
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * args.steps,
             "roofline": roofline, "memory_kernels": mem, "kernel_ms_per_chunk": step_ms, "cpu_baseline": cpu}))
     if world > 1:

@@ -63,6 +63,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// One elected lane of a converged warp (PTX elect.sync).  ptxas knows the guarded region is
+// single-threaded and keeps descriptors in uniform registers; a `lane == 0` test instead makes
+// it wrap every tcgen05.mma in an ELECT/branch loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -135,10 +149,11 @@ struct UmmaConvParams {
   const float* bias;
   __half* out;
   int relu;
+  int bstages;  // weight block ring depth (2..4)
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
-constexpr int kBStages = 4;    // weight block stages
+constexpr int kMaxBStages = 4; // weight block stages (ring depth is a launch parameter, <= 4)
 constexpr int kThreads = 224;  // 7 warps
 constexpr int kTailPad = 2304; // dense M tiles may read up to 129 voxel records past the last plane
 constexpr int kBufCols = 256;  // TMEM columns per accumulator buffer (2 buffers)
@@ -173,7 +188,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   uint8_t* sA = smem;
   uint8_t* sB = smem + kRing * p.slot_stride;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + kBStages * Cfg::BSTAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.bstages * Cfg::BSTAGE);
   // barrier map: [0..2] a_full, [3..5] a_empty, [6..9] b_full, [10..13] b_empty, [14,15] acc_full, [16,17] acc_empty
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -181,7 +196,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(10 + i), 1); }
+    for (int i = 0; i < kMaxBStages; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(10 + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(14 + i), 1); mbar_init(BAR(16 + i), 128); }
     fence_barrier_init();
     fence_proxy_async();
@@ -198,7 +213,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int Z = p.Z;
   if (warp == 0) {
     // ---------------- A producer: z-planes -1 .. Z into the ring ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
       const int plane_a0 = b * p.planes_a * P, plane_b0 = b * p.planes_b * P;
       for (int q = 0; q < Z + 2; ++q) {
@@ -214,12 +229,13 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp == 1) {
     // ---------------- B producer: weight blocks, 27 * KG per z-plane job ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t total = (uint32_t)Z * 27u * Cfg::KG;
       const uint32_t per_job = 27u * Cfg::KG;
+      const uint32_t nbs = (uint32_t)p.bstages;
       for (uint32_t i = 0; i < total; ++i) {
-        const uint32_t st = i % kBStages;
-        if (i >= kBStages) mbar_wait(BAR(10 + st), ((i / kBStages) - 1) & 1);
+        const uint32_t st = i % nbs;
+        if (i >= nbs) mbar_wait(BAR(10 + st), ((i / nbs) - 1) & 1);
         mbar_expect_tx(BAR(6 + st), Cfg::BSTAGE);
         bulk_load(smem_u32(sB + st * Cfg::BSTAGE),
                   reinterpret_cast<const uint8_t*>(p.wpacked) + (size_t)(i % per_job) * Cfg::BSTAGE, Cfg::BSTAGE,
@@ -228,13 +244,14 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     }
   } else if (warp == 2) {
     // ---------------- MMA issuer ----------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t IDESC1 = make_idesc(Cfg::NB);
       constexpr uint32_t IDESC2 = make_idesc(COUT);
       const uint32_t plane16 = p.plane_stride >> 4;
       const uint32_t sA16 = smem_u32(sA) >> 4, slot16 = p.slot_stride >> 4;
       const uint32_t sB16 = smem_u32(sB) >> 4;
       uint32_t bi = 0;
+      const uint32_t nbs = (uint32_t)p.bstages;
       for (int z = 0; z < Z; ++z) {
         const int buf = z & 1;
         if (z >= 2) mbar_wait(BAR(16 + buf), ((z >> 1) - 1) & 1);
@@ -247,8 +264,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           for (int t9 = 0; t9 < 9; ++t9) {
             const uint32_t tapoff = (uint32_t)((t9 / 3) * p.pitch + (t9 % 3));
             for (int kg = 0; kg < Cfg::KG; ++kg, ++bi) {
-              const uint32_t st = bi % kBStages;
-              mbar_wait(BAR(6 + st), (bi / kBStages) & 1);
+              const uint32_t st = bi % nbs;
+              mbar_wait(BAR(6 + st), (bi / nbs) & 1);
               tc_fence_after();
               const uint32_t b16 = sB16 + st * (Cfg::BSTAGE >> 4);
 #pragma unroll
@@ -381,32 +398,48 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
   UmmaConvParams p{};
   p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
-  p.XT = std::min(sz.x, 128);
+  // Tile search: x tile XT (<= 128 voxels per TMA box row), even row count TY, weight ring depth.
+  // Cost = shared-memory traffic amplification: halo rows/cols re-read plus junk M-tile positions.
+  double best_cost = 1e30;
+  int best_xt = 0, best_ty = 0, best_bs = 0;
+  const int ty_cap = std::min(16, (sz.y + 1) & ~1);
+  for (int xt : {128, 64, 32}) {
+    if (xt > sz.x && xt != 128) continue;
+    const int XT = std::min(sz.x, xt);
+    const int pitch = XT + 2 + (XT & 1);
+    const bool aligned = XT == 128;
+    for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
+      const size_t plane = (size_t)(tyc + 2) * pitch * 16;
+      const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
+      const int G = aligned ? tyc : ceil_div(tyc * pitch, 128);
+      if (G > Cfg::MAXG || slot >= (1u << 18)) continue;
+      for (int bs = kMaxBStages; bs >= 2; --bs) {
+        const size_t total = (size_t)kRing * slot + (size_t)bs * Cfg::BSTAGE + 256 + kTailPad + 128;
+        if (total > (size_t)kMaxSmem) continue;
+        const int ty_eff = std::min(tyc, sz.y);
+        const double useful = (double)ty_eff * XT;
+        const double cost = ((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) +
+                            (bs < 3 ? 0.25 : 0.0);
+        if (cost < best_cost) { best_cost = cost; best_xt = XT; best_ty = tyc; best_bs = bs; }
+        break;  // deeper rings are never worse; take the deepest that fits
+      }
+    }
+  }
+  if (!best_ty) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
+  p.XT = best_xt;
   p.pitch = p.XT + 2 + (p.XT & 1);
   const bool row_aligned = p.XT == 128;
   p.tile_stride = row_aligned ? p.pitch : 128;
   p.tiles_x = ceil_div(sz.x, p.XT);
-  const int fixed = kBStages * Cfg::BSTAGE + 256 + kTailPad + 128;
-  int best_ty = 0;
-  const int ty_cap = std::min(16, (sz.y + 1) & ~1);
-  for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
-    const size_t plane = (size_t)(tyc + 2) * p.pitch * 16;
-    const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
-    const int G = row_aligned ? tyc : ceil_div(tyc * p.pitch, 128);
-    if ((size_t)kRing * slot + fixed <= (size_t)kMaxSmem && G <= Cfg::MAXG && tyc + 2 <= 256 && slot < (1u << 18)) {
-      best_ty = tyc;
-      break;
-    }
-  }
-  if (!best_ty) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
   p.TY = best_ty;
+  p.bstages = best_bs;
   p.G = row_aligned ? p.TY : ceil_div(p.TY * p.pitch, 128);
   p.tiles_y = ceil_div(sz.y, p.TY);
   p.plane_stride = (uint32_t)((p.TY + 2) * p.pitch * 16);
   p.slot_stride = (uint32_t)((Cfg::NPL * (size_t)p.plane_stride + 127) / 128 * 128);
   p.planes_a = ca / 8; p.planes_b = cb / 8;
   p.wpacked = w.w; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
-  const size_t smem = (size_t)kRing * p.slot_stride + fixed;
+  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * Cfg::BSTAGE + 256 + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P) : mapA;
   auto kern = conv3_umma_kernel<CIN, COUT, SPLIT>;

@@ -12,9 +12,13 @@ pytestmark = pytest.mark.gpu
 # identity / blend arithmetic is fp32 with atomics in arbitrary order: ~1 ulp of the sums
 BLEND_ATOL = 2e-6
 # fp32 SIMT convolutions vs torch-CPU: different summation order only
-NET_ATOL_F32 = 2e-5
-# north_star tolerance for the tensor-core path
+NET_ATOL_SIMT = 2e-5
+# default mode (tcgen05, fp16 hi/lo split, fp32 accumulate): measured 2e-5 .. 4e-5; the bar in
+# BASELINE.json's north_star is 1e-3 max-abs -- assert 5x tighter than that
+NET_ATOL_F32 = 2e-4
 NET_ATOL = 1e-3
+# single-pass fp16 (reference --dtype float16): operands and stored activations carry 11 bits
+NET_ATOL_F16 = 2e-2
 
 
 def _inferencer(**kw):
@@ -90,15 +94,19 @@ def test_reference_test_time_augmentation_identity():
     np.testing.assert_allclose(out.array, o, rtol=0, atol=BLEND_ATOL)
 
 
-def test_unet3l_golden(golden):
+@pytest.mark.parametrize("precision,dtype,atol", [(None, "float32", NET_ATOL_F32), ("simt", "float32", NET_ATOL_SIMT),
+                                                  ("f16x3", "float32", NET_ATOL_F32), (None, "float16", NET_ATOL_F16)])
+def test_unet3l_golden(golden, precision, dtype, atol):
+    """The reference's own `-f pytorch` CPU output (golden) against every precision mode."""
     g = golden("unet3l_small.npz")
     for batch in (1, 4):
         inf = _inferencer(model=MODEL_FILE, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8),
-                          num_output_channels=3, batch_size=batch, framework="pytorch", mask_output_chunk=True)
+                          num_output_channels=3, batch_size=batch, framework="pytorch", mask_output_chunk=True,
+                          precision=precision, dtype=dtype)
         out = inf(Chunk(g["input"]))
         err = np.abs(out.array - g["output"]).max()
-        print("unet3l golden max-abs", err)
-        assert err <= NET_ATOL_F32
+        print("unet3l golden max-abs", precision, dtype, err)
+        assert err <= atol
 
 
 def test_unet3l_readme_config_against_oracle(unet_model):
@@ -115,18 +123,42 @@ def test_unet3l_readme_config_against_oracle(unet_model):
     assert inf.timing["launches"] > 0
 
 
-@pytest.mark.parametrize("cin,cout,size", [(1, 16, (5, 20, 36)), (16, 16, (4, 16, 70)), (48, 32, (3, 9, 13)), (64, 64, (6, 8, 8))])
-def test_conv3_layer_against_torch(cin, cout, size):
+def _conv3_case(prec, cin, cout, size, atol, round_operands=False):
     import torch
     rng = np.random.default_rng(cin * 100 + cout)
     x = rng.standard_normal((cin,) + size).astype(np.float32)
     w = (rng.standard_normal((cout, cin, 3, 3, 3)) / np.sqrt(27 * cin)).astype(np.float32)
     b = rng.standard_normal(cout).astype(np.float32)
     eng = _native.Engine(input_patch_size=(8, 32, 32), output_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8),
-                         output_crop_margin=(0, 0, 0), framework=_native.FRAMEWORK_IDENTITY)
+                         output_crop_margin=(0, 0, 0), framework=_native.FRAMEWORK_IDENTITY, precision=prec)
     got = eng.debug_conv3(x, w, b, relu=True)
-    ref = torch.relu(torch.nn.functional.conv3d(torch.from_numpy(x)[None], torch.from_numpy(w), torch.from_numpy(b), padding=1))[0].numpy()
-    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)
+    xt, wt = torch.from_numpy(x), torch.from_numpy(w)
+    ref = torch.relu(torch.nn.functional.conv3d(xt[None], wt, torch.from_numpy(b), padding=1))[0].numpy()
+    np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
+
+
+@pytest.mark.parametrize("cin,cout,size", [(1, 16, (5, 20, 36)), (16, 16, (4, 16, 70)), (48, 32, (3, 9, 13)), (64, 64, (6, 8, 8))])
+def test_conv3_layer_simt_against_torch(cin, cout, size):
+    _conv3_case(_native.PRECISION_F32_SIMT, cin, cout, size, 2e-5)
+
+
+# (cin, cout, size): dense M tiles with junk columns, row-aligned 128-voxel tiles with two x tiles,
+# two-source (concat) inputs, ragged x/y extents, every channel configuration of the network
+UMMA_CASES = [(16, 16, (3, 8, 40)), (16, 16, (4, 16, 70)), (32, 32, (3, 12, 20)), (16, 32, (2, 6, 128)),
+              (16, 16, (5, 20, 256)), (64, 64, (6, 8, 8)), (64, 32, (4, 16, 16)), (32, 16, (3, 8, 130)), (32, 64, (3, 9, 64)),
+              (16, 16, (2, 7, 9))]
+
+
+@pytest.mark.parametrize("cin,cout,size", UMMA_CASES)
+def test_conv3_layer_tcgen05_split_against_torch(cin, cout, size):
+    # hi/lo split operands: ~22 significant bits, fp32 accumulation in TMEM
+    _conv3_case(_native.PRECISION_F16X3_UMMA, cin, cout, size, 5e-5)
+
+
+@pytest.mark.parametrize("cin,cout,size", UMMA_CASES[:4])
+def test_conv3_layer_tcgen05_fp16_against_torch(cin, cout, size):
+    # single-pass fp16: 11-bit operands and 11-bit stored outputs on values of magnitude ~5
+    _conv3_case(_native.PRECISION_F16_UMMA, cin, cout, size, 1e-2)
 
 
 def test_plugin_level_patch_inferencer(unet_model):

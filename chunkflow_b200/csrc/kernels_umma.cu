@@ -16,6 +16,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "chunkflow_b200.h"
@@ -89,6 +92,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -121,13 +131,10 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address, leading byte offset (between the two 8-element K chunks) and stride byte
-// offset (between 8-row groups), all in 16-byte units; bits [46,48) = 1 (Blackwell version).
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr16, uint32_t lbo16, uint32_t sbo16) {
-  return (uint64_t)(addr16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) |
-         (1ull << 46);
-}
+// K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor), 64 bits:
+//   [0,14)  start address >> 4      [16,30) leading byte offset >> 4 (between the two 8-element K chunks)
+//   [32,46) stride byte offset >> 4 (between 8-row groups)           [46,48) version = 1 (Blackwell)
+//   [61,64) layout type = 0 (no swizzle).  Built inline in the MMA issuer as a (hi, lo) pair.
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, M=128.
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -149,14 +156,17 @@ struct UmmaConvParams {
   const float* bias;
   __half* out;
   int relu;
-  int bstages;  // weight block ring depth (2..4)
+  int bstages;    // weight block stages in shared memory
+  int bresident;  // 1: all 27*KG blocks stay resident (loaded once per CTA), 0: streamed through a ring
+  int wide_map;   // 1: 5-D tensor map with the 16-byte record as inner dimension, 0: 4-D map over 8-byte elements
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
-constexpr int kMaxBStages = 4; // weight block stages (ring depth is a launch parameter, <= 4)
+constexpr int kMaxBStages = 64; // weight block stages: resident (27 * KG <= 54 blocks) or a ring of up to 64
 constexpr int kThreads = 224;  // 7 warps
 constexpr int kTailPad = 2304; // dense M tiles may read up to 129 voxel records past the last plane
 constexpr int kBufCols = 256;  // TMEM columns per accumulator buffer (2 buffers)
+constexpr int kBarBytes = (10 + 2 * 64) * 8 + 16;  // mbarriers + TMEM base slot
 
 template <int CIN, int COUT, bool SPLIT>
 struct ConvCfg {
@@ -189,15 +199,17 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   uint8_t* sA = smem;
   uint8_t* sB = smem + kRing * p.slot_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.bstages * Cfg::BSTAGE);
-  // barrier map: [0..2] a_full, [3..5] a_empty, [6..9] b_full, [10..13] b_empty, [14,15] acc_full, [16,17] acc_empty
+  // barrier map: [0..2] a_full, [3..5] a_empty, [6,7] acc_full, [8,9] acc_empty,
+  //              [10, 10+64) b_full, [74, 74+64) b_empty
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  constexpr int kBF = 10, kBE = 10 + kMaxBStages, kAccF = 6, kAccE = 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBE + kMaxBStages);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-    for (int i = 0; i < kMaxBStages; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(10 + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(14 + i), 1); mbar_init(BAR(16 + i), 128); }
+    for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), 1); mbar_init(BAR(kAccE + i), 128); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -216,30 +228,38 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
       const int plane_a0 = b * p.planes_a * P, plane_b0 = b * p.planes_b * P;
-      for (int q = 0; q < Z + 2; ++q) {
-        const int slot = q % kRing;
-        if (q >= kRing) mbar_wait(BAR(3 + slot), ((q / kRing) - 1) & 1);
+      int slot = 0;
+      uint32_t use_parity = 1;  // parity of the PREVIOUS use of the slot (no wait during the first round)
+      for (int q = 0; q < Z + 2; ++q, ++slot) {
+        if (slot == kRing) { slot = 0; use_parity ^= 1; }
+        if (q >= kRing) mbar_wait(BAR(3 + slot), use_parity);
         mbar_expect_tx(BAR(slot), tx_bytes);
         const uint32_t dst = smem_u32(sA + (size_t)slot * p.slot_stride);
-        tma_load_5d(dst, &mapA, BAR(slot), 0, x0 - 1, y0 - 1, q - 1, plane_a0);
-        if (p.planes_b > 0)
-          tma_load_5d(dst + (uint32_t)(p.planes_a * P) * p.plane_stride, &mapB, BAR(slot), 0, x0 - 1, y0 - 1, q - 1,
-                      plane_b0);
+        const uint32_t dst_b = dst + (uint32_t)(p.planes_a * P) * p.plane_stride;
+        if (p.wide_map) {  // 5-D map, 16-byte record as inner dimension (box rows of up to 256 records)
+          tma_load_5d(dst, &mapA, BAR(slot), 0, x0 - 1, y0 - 1, q - 1, plane_a0);
+          if (p.planes_b > 0) tma_load_5d(dst_b, &mapB, BAR(slot), 0, x0 - 1, y0 - 1, q - 1, plane_b0);
+        } else {           // 4-D map over 8-byte elements: a record is two elements (see make_map)
+          tma_load_4d(dst, &mapA, BAR(slot), 2 * (x0 - 1), y0 - 1, q - 1, plane_a0);
+          if (p.planes_b > 0) tma_load_4d(dst_b, &mapB, BAR(slot), 2 * (x0 - 1), y0 - 1, q - 1, plane_b0);
+        }
       }
     }
   } else if (warp == 1) {
     // ---------------- B producer: weight blocks, 27 * KG per z-plane job ----------------
     if (elect_one()) {
-      const uint32_t total = (uint32_t)Z * 27u * Cfg::KG;
       const uint32_t per_job = 27u * Cfg::KG;
       const uint32_t nbs = (uint32_t)p.bstages;
+      // resident: every block is loaded exactly once; ring: blocks stream in job order
+      const uint32_t total = p.bresident ? per_job : (uint32_t)Z * per_job;
+      uint32_t st = 0, blk = 0, prev_parity = 1;
       for (uint32_t i = 0; i < total; ++i) {
-        const uint32_t st = i % nbs;
-        if (i >= nbs) mbar_wait(BAR(10 + st), ((i / nbs) - 1) & 1);
-        mbar_expect_tx(BAR(6 + st), Cfg::BSTAGE);
+        if (i >= nbs) mbar_wait(BAR(kBE + st), prev_parity);
+        mbar_expect_tx(BAR(kBF + st), Cfg::BSTAGE);
         bulk_load(smem_u32(sB + st * Cfg::BSTAGE),
-                  reinterpret_cast<const uint8_t*>(p.wpacked) + (size_t)(i % per_job) * Cfg::BSTAGE, Cfg::BSTAGE,
-                  BAR(6 + st));
+                  reinterpret_cast<const uint8_t*>(p.wpacked) + (size_t)blk * Cfg::BSTAGE, Cfg::BSTAGE, BAR(kBF + st));
+        if (++st == nbs) { st = 0; prev_parity ^= 1; }
+        if (++blk == per_job) blk = 0;
       }
     }
   } else if (warp == 2) {
@@ -247,46 +267,70 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     if (elect_one()) {
       constexpr uint32_t IDESC1 = make_idesc(Cfg::NB);
       constexpr uint32_t IDESC2 = make_idesc(COUT);
+      // Descriptors are (hi, lo) 32-bit pairs; hi is constant (SBO = 128 B, version 1), lo holds the
+      // start address and the leading byte offset, so stepping a tap / tile / K step is one integer add.
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
       const uint32_t plane16 = p.plane_stride >> 4;
+      const uint32_t a_lbo = (P * plane16) << 16;
+      constexpr uint32_t b_lbo = (uint32_t)Cfg::NB << 16;
       const uint32_t sA16 = smem_u32(sA) >> 4, slot16 = p.slot_stride >> 4;
       const uint32_t sB16 = smem_u32(sB) >> 4;
-      uint32_t bi = 0;
+      const uint32_t pitch = (uint32_t)p.pitch, tstride = (uint32_t)p.tile_stride, G = (uint32_t)p.G;
+      const uint32_t kstep16 = 2u * P * plane16;  // two 8-channel chunks per K = 16 step
+      const bool resident = p.bresident != 0;
       const uint32_t nbs = (uint32_t)p.bstages;
+      auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+      uint32_t ring_st = 0, ring_parity = 0;
+      uint32_t slot_lo = 0, slot_parity = 0;  // ring slot / parity of plane q = z (first plane of the job)
       for (int z = 0; z < Z; ++z) {
-        const int buf = z & 1;
-        if (z >= 2) mbar_wait(BAR(16 + buf), ((z >> 1) - 1) & 1);
+        const uint32_t buf = (uint32_t)z & 1u;
+        if (z >= 2) mbar_wait(BAR(kAccE + buf), ((z >> 1) - 1) & 1);
         tc_fence_after();
+        uint32_t acc = 0;  // the first K step of the job overwrites the accumulators
+        uint32_t blk = 0;
+        uint32_t slot = slot_lo, sparity = slot_parity;
+        const uint32_t d0 = tmem_base + buf * kBufCols;
         for (int dz = 0; dz < 3; ++dz) {
-          const int q = z + dz, slot = q % kRing;
-          mbar_wait(BAR(slot), (q / kRing) & 1);
+          mbar_wait(BAR(slot), sparity);
           tc_fence_after();
-          const uint32_t a_slot16 = sA16 + slot * slot16;
-          for (int t9 = 0; t9 < 9; ++t9) {
-            const uint32_t tapoff = (uint32_t)((t9 / 3) * p.pitch + (t9 % 3));
-            for (int kg = 0; kg < Cfg::KG; ++kg, ++bi) {
-              const uint32_t st = bi % nbs;
-              mbar_wait(BAR(6 + st), (bi / nbs) & 1);
-              tc_fence_after();
-              const uint32_t b16 = sB16 + st * (Cfg::BSTAGE >> 4);
+          uint32_t a_row = a_lbo | (sA16 + slot * slot16);
+          for (int dy = 0; dy < 3; ++dy, a_row += pitch) {
+            for (uint32_t dx = 0; dx < 3; ++dx) {
+              const uint32_t a_tap = a_row + dx;
+              for (int kg = 0; kg < Cfg::KG; ++kg) {
+                uint32_t b16;
+                if (resident) {
+                  if (z == 0) { mbar_wait(BAR(kBF + blk), 0); tc_fence_after(); }  // blocks arrive once
+                  b16 = sB16 + blk * (Cfg::BSTAGE >> 4);
+                  ++blk;
+                } else {
+                  mbar_wait(BAR(kBF + ring_st), ring_parity);
+                  tc_fence_after();
+                  b16 = sB16 + ring_st * (Cfg::BSTAGE >> 4);
+                }
 #pragma unroll
-              for (int ks = 0; ks < Cfg::KS; ++ks) {
-                const uint32_t chunk0 = (uint32_t)(kg * Cfg::KS + ks) * 2u;
-                const uint64_t bdesc = make_desc(b16 + (uint32_t)ks * 2u * Cfg::NB, Cfg::NB, 8);
-                const uint32_t a_k16 = a_slot16 + chunk0 * P * plane16 + tapoff;
-                const uint32_t first = (dz == 0 && t9 == 0 && kg == 0 && ks == 0) ? 0u : 1u;
-                for (int g = 0; g < p.G; ++g) {
-                  const uint32_t a16 = a_k16 + (uint32_t)(g * p.tile_stride);
-                  const uint32_t d = tmem_base + (uint32_t)(buf * kBufCols + g * Cfg::NB);
-                  tc_mma_f16(d, make_desc(a16, P * plane16, 8), bdesc, IDESC1, first);
-                  if (SPLIT) tc_mma_f16(d, make_desc(a16 + plane16, P * plane16, 8), bdesc, IDESC2, 1u);
+                for (int ks = 0; ks < Cfg::KS; ++ks) {
+                  const uint64_t bdesc = desc(b_lbo | (b16 + (uint32_t)ks * 2u * Cfg::NB));
+                  uint32_t a_lo = a_tap + (uint32_t)(kg * Cfg::KS + ks) * kstep16;
+                  uint32_t d = d0;
+                  for (uint32_t g = 0; g < G; ++g, a_lo += tstride, d += Cfg::NB) {
+                    tc_mma_f16(d, desc(a_lo), bdesc, IDESC1, acc);
+                    if (SPLIT) tc_mma_f16(d, desc(a_lo + plane16), bdesc, IDESC2, 1u);
+                  }
+                  acc = 1;
+                }
+                if (!resident) {
+                  tc_commit(BAR(kBE + ring_st));  // weight block consumed
+                  if (++ring_st == nbs) { ring_st = 0; ring_parity ^= 1; }
                 }
               }
-              tc_commit(BAR(10 + st));  // weight block consumed
             }
           }
           if (dz == 0) tc_commit(BAR(3 + slot));  // plane z-1 is dead: the producer may refill its slot
+          if (++slot == kRing) { slot = 0; sparity ^= 1; }
         }
-        tc_commit(BAR(14 + buf));  // accumulators of this z-plane are complete
+        tc_commit(BAR(kAccF + buf));  // accumulators of this z-plane are complete
+        if (++slot_lo == kRing) { slot_lo = 0; slot_parity ^= 1; }
       }
     }
   } else {
@@ -294,15 +338,17 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int wq = warp & 3;  // TMEM lane quarter this warp may access
     const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
     const size_t plane_vox = (size_t)p.Z * p.Y * p.X;
+    const float inv_pitch = 1.0f / (float)p.pitch;
     uint4* out16 = reinterpret_cast<uint4*>(p.out);
     for (int z = 0; z < Z; ++z) {
       const int buf = z & 1;
-      mbar_wait(BAR(14 + buf), (z >> 1) & 1);
+      mbar_wait(BAR(kAccF + buf), (z >> 1) & 1);
       tc_fence_after();
       for (int g = 0; g < p.G; ++g) {
         const int m = wq * 32 + lane;
         const int qpos = g * p.tile_stride + m;
-        const int row = qpos / p.pitch, col = qpos - row * p.pitch;
+        // exact for qpos < 2^20: (qpos + 0.5) / pitch never lands within rounding error of an integer
+        const int row = __float2int_rd(((float)qpos + 0.5f) * inv_pitch), col = qpos - row * p.pitch;
         const bool valid = row < ty_valid && col < xt_valid;
         const size_t vox = ((size_t)z * p.Y + (y0 + row)) * p.X + (x0 + col);
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kBufCols + g * Cfg::NB);
@@ -349,7 +395,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR(16 + buf));
+      mbar_arrive(BAR(kAccE + buf));
     }
   }
 
@@ -376,76 +422,169 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-// CP8 tensor (planes, Z, Y, X, 8) fp16 -> 5-D tensor map with box (8, bx, by, 1, bplanes)
-CUtensorMap make_map(const __half* base, int planes, Int3 sz, int bx, int by, int bplanes) {
+// CP8 tensor (planes, Z, Y, X, 8 x fp16) as a TMA tensor map.  Two flavours:
+//  * narrow (4-D over 8-byte elements): the 16-byte voxel records of one x row are contiguous in
+//    memory, so (x, channel) is ONE inner dimension of 2*X uint64 elements and a box row is one
+//    contiguous run (full 32-byte sectors; box rows limited to 256 elements = 128 records);
+//  * wide (5-D, the 16-byte record is the inner dimension): box rows of up to 256 records, but
+//    the TMA engine fetches one 32-byte sector per record (2x the L2->SM traffic).
+// Out-of-bounds elements are zero-filled either way: SAME padding at the patch border.
+CUtensorMap make_map(const __half* base, int planes, Int3 sz, int bx, int by, int bplanes, bool wide) {
   CUtensorMap m;
-  cuuint64_t gdim[5] = {8, (cuuint64_t)sz.x, (cuuint64_t)sz.y, (cuuint64_t)sz.z, (cuuint64_t)planes};
-  cuuint64_t gstr[4] = {16, (cuuint64_t)sz.x * 16, (cuuint64_t)sz.x * sz.y * 16, (cuuint64_t)sz.x * sz.y * sz.z * 16};
-  cuuint32_t box[5] = {8, (cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)bplanes};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (wide) {
+    cuuint64_t gdim[5] = {8, (cuuint64_t)sz.x, (cuuint64_t)sz.y, (cuuint64_t)sz.z, (cuuint64_t)planes};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)sz.x * 16, (cuuint64_t)sz.x * sz.y * 16, (cuuint64_t)sz.x * sz.y * sz.z * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)bx, (cuuint32_t)by, 1, (cuuint32_t)bplanes};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    if (bx > 128) throw std::runtime_error("narrow TMA box row limited to 128 voxel records");
+    cuuint64_t gdim[4] = {(cuuint64_t)sz.x * 2, (cuuint64_t)sz.y, (cuuint64_t)sz.z, (cuuint64_t)planes};
+    cuuint64_t gstr[3] = {(cuuint64_t)sz.x * 16, (cuuint64_t)sz.x * sz.y * 16, (cuuint64_t)sz.x * sz.y * sz.z * 16};
+    cuuint32_t box[4] = {(cuuint32_t)bx * 2, (cuuint32_t)by, 1, (cuuint32_t)bplanes};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<__half*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   return m;
 }
 
 constexpr int kMaxSmem = 232448;  // 227 KB
 
+// All feasible tilings of one layer, cheapest first by a static cost model:
+//   (halo amplification of the z-plane loads)/2 + (M-tile positions per useful output), scaled by
+//   the wave quantisation of the grid, + a penalty for shallow weight rings.
 template <int CIN, int COUT, bool SPLIT>
-void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
-                Int3 sz, bool relu, cudaStream_t s) {
+std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
-  UmmaConvParams p{};
-  p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
-  // Tile search: x tile XT (<= 128 voxels per TMA box row), even row count TY, weight ring depth.
-  // Cost = shared-memory traffic amplification: halo rows/cols re-read plus junk M-tile positions.
-  double best_cost = 1e30;
-  int best_xt = 0, best_ty = 0, best_bs = 0;
+  std::vector<ConvTile> out;
   const int ty_cap = std::min(16, (sz.y + 1) & ~1);
-  for (int xt : {128, 64, 32}) {
-    if (xt > sz.x && xt != 128) continue;
-    const int XT = std::min(sz.x, xt);
-    const int pitch = XT + 2 + (XT & 1);
-    const bool aligned = XT == 128;
+  std::vector<std::pair<int, bool>> xts;  // (XT, wide map)
+  if (sz.x >= 128) xts.push_back({128, true});
+  for (int k = 1; k <= 16; ++k) {
+    int xt = ceil_div(sz.x, k);
+    xt += xt & 1;
+    if (xt + 2 > 128 || (xt < 16 && k > 1)) continue;
+    bool dup = false;
+    for (auto& e : xts) dup |= (e.first == xt && !e.second);
+    if (!dup) xts.push_back({xt, false});
+  }
+  for (auto& e : xts) {
+    const int XT = e.first, pitch = XT + 2;
+    const bool aligned = XT == 128;  // one 128-voxel M tile per row; otherwise dense 128-position runs
     for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
       const size_t plane = (size_t)(tyc + 2) * pitch * 16;
       const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
       const int G = aligned ? tyc : ceil_div(tyc * pitch, 128);
       if (G > Cfg::MAXG || slot >= (1u << 18)) continue;
-      for (int bs = kMaxBStages; bs >= 2; --bs) {
-        const size_t total = (size_t)kRing * slot + (size_t)bs * Cfg::BSTAGE + 256 + kTailPad + 128;
-        if (total > (size_t)kMaxSmem) continue;
-        const int ty_eff = std::min(tyc, sz.y);
-        const double useful = (double)ty_eff * XT;
-        const double cost = ((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) +
-                            (bs < 3 ? 0.25 : 0.0);
-        if (cost < best_cost) { best_cost = cost; best_xt = XT; best_ty = tyc; best_bs = bs; }
-        break;  // deeper rings are never worse; take the deepest that fits
-      }
+      const size_t fixed = (size_t)kBarBytes + kTailPad + 128;
+      if ((size_t)kRing * slot + fixed >= (size_t)kMaxSmem) continue;
+      const size_t room = (size_t)kMaxSmem - (size_t)kRing * slot - fixed;
+      const int all_blocks = 27 * Cfg::KG;
+      int bs = (int)std::min<size_t>(room / Cfg::BSTAGE, kMaxBStages);
+      if (bs >= all_blocks) bs = all_blocks;
+      if (bs < 3) continue;
+      ConvTile t;
+      t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
+      const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
+      const double lookahead = t.resident ? 1e9 : (double)(bs - 1) * G * Cfg::KS * Cfg::P;
+      const int ctas = nb * ceil_div(sz.x, XT) * ceil_div(sz.y, tyc);
+      const double waves = (double)ctas / sm_count;
+      const double quant = std::ceil(waves) / waves;
+      t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful)) * quant +
+               (lookahead >= 96 ? 0.0 : 0.4 * (96 - lookahead) / 96);
+      out.push_back(t);
     }
   }
-  if (!best_ty) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
-  p.XT = best_xt;
-  p.pitch = p.XT + 2 + (p.XT & 1);
+  std::sort(out.begin(), out.end(), [](const ConvTile& a, const ConvTile& b) { return a.cost < b.cost; });
+  return out;
+}
+
+template <int CIN, int COUT, bool SPLIT>
+void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w,
+                 __half* out, int nb, Int3 sz, bool relu, cudaStream_t s) {
+  using Cfg = ConvCfg<CIN, COUT, SPLIT>;
+  UmmaConvParams p{};
+  p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
+  p.XT = t.XT;
+  p.pitch = p.XT + 2;
   const bool row_aligned = p.XT == 128;
   p.tile_stride = row_aligned ? p.pitch : 128;
   p.tiles_x = ceil_div(sz.x, p.XT);
-  p.TY = best_ty;
-  p.bstages = best_bs;
+  p.TY = t.TY;
+  p.bstages = t.bstages;
+  p.bresident = t.resident ? 1 : 0;
+  p.wide_map = t.wide ? 1 : 0;
   p.G = row_aligned ? p.TY : ceil_div(p.TY * p.pitch, 128);
   p.tiles_y = ceil_div(sz.y, p.TY);
   p.plane_stride = (uint32_t)((p.TY + 2) * p.pitch * 16);
   p.slot_stride = (uint32_t)((Cfg::NPL * (size_t)p.plane_stride + 127) / 128 * 128);
   p.planes_a = ca / 8; p.planes_b = cb / 8;
   p.wpacked = w.w; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
-  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * Cfg::BSTAGE + 256 + kTailPad + 128;
-  const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P);
-  const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P) : mapA;
+  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * Cfg::BSTAGE + kBarBytes + kTailPad + 128;
+  const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
+  const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
   auto kern = conv3_umma_kernel<CIN, COUT, SPLIT>;
   CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, mapB, p);
   CFB_LAUNCH_CHECK();
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    CFB_CUDA(cudaGetDevice(&dev));
+    CFB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+// First launch of a (layer, size, batch): time the most promising tilings on the real buffers (every
+// tiling computes bit-identical results) and cache the winner in the layer's PackedConv.
+template <int CIN, int COUT, bool SPLIT>
+void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
+                Int3 sz, bool relu, cudaStream_t s) {
+  const uint64_t key = ((uint64_t)sz.z << 48) ^ ((uint64_t)sz.y << 32) ^ ((uint64_t)sz.x << 16) ^ (uint64_t)nb;
+  auto it = w.tuned->find(key);
+  if (it == w.tuned->end()) {
+    std::vector<ConvTile> cands = enumerate_tiles<CIN, COUT, SPLIT>(nb, sz, sm_count());
+    if (cands.empty()) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
+    ConvTile best = cands[0];
+    const int64_t work = (int64_t)nb * vol(sz);
+    const bool tune = !getenv("CFB_NO_AUTOTUNE") && work >= (1 << 18) && cands.size() > 1;
+    if (tune) {
+      cudaEvent_t e0, e1;
+      CFB_CUDA(cudaEventCreate(&e0));
+      CFB_CUDA(cudaEventCreate(&e1));
+      float best_ms = 1e30f;
+      const size_t n = std::min<size_t>(cands.size(), 14);
+      for (size_t i = 0; i < n; ++i) {
+        launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
+        CFB_CUDA(cudaEventRecord(e0, s));
+        launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+        CFB_CUDA(cudaEventRecord(e1, s));
+        CFB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best_ms) { best_ms = ms; best = cands[i]; }
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      best.cost = best_ms;
+    }
+    if (getenv("CFB_DEBUG_CFG"))
+      fprintf(stderr, "[cfb] conv3 %d->%d split=%d size=%dx%dx%d nb=%d: XT=%d%s TY=%d bstages=%d resident=%d (%s %.3f)\n",
+              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.XT, best.wide ? "w" : "", best.TY, best.bstages,
+              (int)best.resident, tune ? "tuned ms" : "model cost", best.cost);
+    it = w.tuned->emplace(key, best).first;
+  }
+  launch_tile<CIN, COUT, SPLIT>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
 }
 
 template <bool SPLIT>
@@ -489,6 +628,7 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
             buf[((size_t)t * KG + g) * block + ((size_t)kc * NB + n) * 8 + e] = val;
           }
   out.cin = cin; out.cout = cout; out.parts = parts;
+  out.tuned = std::make_shared<std::map<uint64_t, ConvTile>>();
   out.bytes = buf.size() * sizeof(__half);
   CFB_CUDA(cudaMalloc(&out.w, out.bytes));
   CFB_CUDA(cudaMemcpy(out.w, buf.data(), out.bytes, cudaMemcpyHostToDevice));

@@ -13,17 +13,29 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include <map>
+#include <memory>
+
 #include "common.cuh"
 
 namespace cfb {
 
 // Weights of one 3x3x3 layer packed for the B operand: for tap t (27), K-group g:
 // [KB/8][NB rows][8] fp16, rows 0..COUT-1 = fp16(w), rows COUT..2COUT-1 = fp16(w - fp16(w)) (split only).
+// One tiling of the tcgen05 convolution (see kernels_umma.cu): x tile, rows per tile, weight block
+// stages, resident weights, TMA map flavour.
+struct ConvTile {
+  int XT = 0, TY = 0, bstages = 0;
+  bool resident = false, wide = false;
+  double cost = 0.0;
+};
+
 struct PackedConv {
   __half* w = nullptr;  // device
   float* bias = nullptr;
   int cin = 0, cout = 0, parts = 1;
   size_t bytes = 0;
+  std::shared_ptr<std::map<uint64_t, ConvTile>> tuned;  // autotuned tiling per (size, batch)
 };
 
 void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out);

@@ -235,7 +235,9 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     pv = P * int(np.prod(patch))
     mem = {}
-    for name, bytes_per in (("extract", 5 * pv), ("blend", 36 * pv)):
+    parts = {0: 0, 1: 2, 2: 1}[eng.params.precision]
+    # fused head+blend reads the last CP8 activation (16 ch x 2 B x parts) and read-modify-writes 3 fp32 channels
+    for name, bytes_per in (("extract", 5 * pv), ("blend", 36 * pv), ("head+blend", (32 * parts + 24) * pv)):
         if name in layers and layers[name][0] > 0:
             gbs = bytes_per / (layers[name][0] / 1e3) / 1e9
             mem[name] = {"ms_per_chunk": layers[name][0], "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}

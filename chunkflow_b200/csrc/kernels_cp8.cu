@@ -235,6 +235,46 @@ head_sigmoid_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ 
   }
 }
 
+// ---- fused head + sigmoid + crop + mask + blend --------------------------------------------
+// One thread = one voxel of the (cropped) output patch, all output channels.
+__global__ void __launch_bounds__(kT)
+head_blend_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, int cin,
+                      int cnet, int parts, Int3 ip, Int3 op, Int3 crop, const float* __restrict__ mask,
+                      const PatchPos* __restrict__ patches, int nb, float* __restrict__ out, int channels, Int3 os) {
+  extern __shared__ float s_hw[];  // [channels][cin] + [channels]
+  for (int i = threadIdx.x; i < channels * cin; i += blockDim.x) s_hw[i] = w[i];
+  for (int i = threadIdx.x; i < channels; i += blockDim.x) s_hw[channels * cin + i] = bias[i];
+  __syncthreads();
+  const size_t ipvol = (size_t)ip.z * ip.y * ip.x, opvol = (size_t)op.z * op.y * op.x;
+  const size_t out_vol = (size_t)os.z * os.y * os.x;
+  const size_t total = (size_t)nb * opvol;
+  const int chunks = cin / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t ov = i % opvol;
+    const int b = (int)(i / opvol);
+    const int x = (int)(ov % op.x), y = (int)((ov / op.x) % op.y), z = (int)(ov / ((size_t)op.x * op.y));
+    const PatchPos pp = patches[b];
+    const int gz = pp.oz + z, gy = pp.oy + y, gx = pp.ox + x;
+    if (gz < 0 || gz >= os.z || gy < 0 || gy >= os.y || gx < 0 || gx >= os.x) continue;  // clipped
+    const size_t iv = ((size_t)(z + crop.z) * ip.y + (y + crop.y)) * ip.x + (x + crop.x);
+    float acc[8];
+    for (int co = 0; co < channels; ++co) acc[co] = s_hw[channels * cin + co];
+    for (int ch = 0; ch < chunks; ++ch) {
+      float v[8];
+      load8(in, ((size_t)b * chunks + ch) * parts, parts, ipvol, iv, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        for (int co = 0; co < channels; ++co) acc[co] = fmaf(v[e], s_hw[co * cin + ch * 8 + e], acc[co]);
+    }
+    const float m = __ldg(mask + ov);
+    float* dst = out + ((size_t)gz * os.y + gy) * os.x + gx;
+    for (int co = 0; co < channels; ++co) {
+      const float sig = __fdiv_rn(1.0f, 1.0f + expf(-acc[co]));
+      asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)co * out_vol), "f"(sig * m) : "memory");
+    }
+  }
+}
+
 int grid_for(size_t items) {
   size_t b = (items + kT - 1) / kT;
   if (b < 1) b = 1;
@@ -296,6 +336,17 @@ void launch_convT_cp8(const __half* in, const float* w, const float* bias, __hal
   } else {
     throw std::runtime_error("convT_cp8: unsupported cout");
   }
+  CFB_LAUNCH_CHECK();
+}
+
+void launch_head_blend_cp8(const __half* in, const float* w, const float* bias, int cin, int cnet, int parts, Int3 ip,
+                           Int3 op, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out, int channels,
+                           Int3 os, cudaStream_t s) {
+  if (channels > 8 || channels > cnet) throw std::runtime_error("head_blend: bad channel count");
+  const size_t smem = (size_t)(channels * cin + channels) * sizeof(float);
+  // only the first `channels` rows of the head are evaluated (reference patch/base.py:70-74 keeps the first N)
+  head_blend_cp8_kernel<<<grid_for((size_t)nb * vol(op)), kT, smem, s>>>(reinterpret_cast<const uint4*>(in), w, bias, cin, cnet,
+                                                                        parts, ip, op, crop, mask, patches, nb, out, channels, os);
   CFB_LAUNCH_CHECK();
 }
 

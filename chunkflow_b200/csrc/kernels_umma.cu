@@ -407,6 +407,190 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Transposed convolution kernel = stride = (1,2,2) on tcgen05: a plain GEMM per input voxel,
+//   D[voxel, (tap, cout)] = sum_ci A[voxel, ci] * W[ci, cout, tap],   tap = (a, b) in {0,1}^2,
+// followed by a scatter epilogue: tap (a, b) of input voxel (z, y, x) is output voxel
+// (z, 2y+a, 2x+b).  Same pipeline as the 3x3x3 kernel but no halo (box = tile) and one "tap";
+// the weight block rows are ordered [hi: 4 taps x COUT | lo: 4 taps x COUT] so that in split mode
+// MMA1 = a_hi x [w_hi | w_lo] (N = 8*COUT) and MMA2 = a_lo x w_hi (N = 4*COUT, first half).
+// ------------------------------------------------------------------------------------------
+struct UmmaConvTParams {
+  int Z, Y, X;       // INPUT size; output is (Z, 2Y, 2X)
+  int XT, TY, G;     // tile of TY x XT input voxels = G M-tiles of 128 positions (dense, pitch = XT)
+  int tiles_x, tiles_y;
+  int planes;        // 8-channel chunks of the input
+  uint32_t plane_stride, slot_stride;
+  const __half* wpacked;
+  const float* bias;
+  __half* out;
+};
+
+template <int CIN, int COUT, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParams p) {
+  constexpr int P = SPLIT ? 2 : 1;
+  constexpr int NPL = P * CIN / 8;
+  constexpr int N1 = 4 * P * COUT, N2 = 4 * COUT;
+  constexpr int KS = CIN / 16;
+  constexpr int WBYTES = N1 * CIN * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = blockIdx.x % p.tiles_x;
+  const int ty = (blockIdx.x / p.tiles_x) % p.tiles_y;
+  const int b = blockIdx.x / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.XT, y0 = ty * p.TY;
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kRing * p.slot_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + WBYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };  // [0..2] a_full [3..5] a_empty [6,7] acc_full [8,9] acc_empty [10] w_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(8 + i), 128); }
+    mbar_init(BAR(10), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int Z = p.Z;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)NPL * p.plane_stride;
+      int slot = 0;
+      uint32_t prev_parity = 1;
+      for (int z = 0; z < Z; ++z, ++slot) {
+        if (slot == kRing) { slot = 0; prev_parity ^= 1; }
+        if (z >= kRing) mbar_wait(BAR(3 + slot), prev_parity);
+        mbar_expect_tx(BAR(slot), tx_bytes);
+        tma_load_4d(smem_u32(sA + (size_t)slot * p.slot_stride), &mapA, BAR(slot), 2 * x0, y0, z, b * p.planes * P);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_expect_tx(BAR(10), WBYTES);
+      for (int off = 0; off < WBYTES; off += 8192)
+        bulk_load(smem_u32(sB + off), reinterpret_cast<const uint8_t*>(p.wpacked) + off, min(8192, WBYTES - off), BAR(10));
+    }
+  } else if (warp == 2) {
+    if (elect_one()) {
+      constexpr uint32_t IDESC1 = make_idesc(N1);
+      constexpr uint32_t IDESC2 = make_idesc(N2);
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
+      const uint32_t plane16 = p.plane_stride >> 4;
+      const uint32_t a_lbo = (P * plane16) << 16;
+      constexpr uint32_t b_lbo = (uint32_t)N1 << 16;
+      const uint32_t sA16 = smem_u32(sA) >> 4, slot16 = p.slot_stride >> 4, sB16 = smem_u32(sB) >> 4;
+      auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+      mbar_wait(BAR(10), 0);
+      tc_fence_after();
+      uint32_t slot = 0, sparity = 0;
+      for (int z = 0; z < Z; ++z) {
+        const uint32_t buf = (uint32_t)z & 1u;
+        if (z >= 2) mbar_wait(BAR(8 + buf), ((z >> 1) - 1) & 1);
+        mbar_wait(BAR(slot), sparity);
+        tc_fence_after();
+        const uint32_t a0 = a_lbo | (sA16 + slot * slot16);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          // weight block: [CIN/8 chunks][N1 rows][8]; K step ks = chunks 2ks, 2ks+1
+          const uint64_t bdesc = desc(b_lbo | (sB16 + (uint32_t)ks * 2u * N1));
+          uint32_t a_lo = a0 + (uint32_t)ks * 2u * P * plane16;
+          uint32_t d = tmem_base + buf * kBufCols;
+          for (int g = 0; g < p.G; ++g, a_lo += 128, d += N1) {
+            tc_mma_f16(d, desc(a_lo), bdesc, IDESC1, ks == 0 ? 0u : 1u);
+            if (SPLIT) tc_mma_f16(d, desc(a_lo + plane16), bdesc, IDESC2, 1u);
+          }
+        }
+        tc_commit(BAR(3 + slot));
+        tc_commit(BAR(6 + buf));
+        if (++slot == kRing) { slot = 0; sparity ^= 1; }
+      }
+    }
+  } else {
+    const int wq = warp & 3;
+    const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
+    const int OY = 2 * p.Y, OX = 2 * p.X;
+    const size_t oplane_vox = (size_t)p.Z * OY * OX;
+    const float inv_xt = 1.0f / (float)p.XT;
+    uint4* out16 = reinterpret_cast<uint4*>(p.out);
+    for (int z = 0; z < Z; ++z) {
+      const int buf = z & 1;
+      mbar_wait(BAR(6 + buf), (z >> 1) & 1);
+      tc_fence_after();
+      for (int g = 0; g < p.G; ++g) {
+        const int m = wq * 32 + lane;
+        const int qpos = g * 128 + m;
+        const int row = __float2int_rd(((float)qpos + 0.5f) * inv_xt), col = qpos - row * p.XT;
+        const bool valid = row < ty_valid && col < xt_valid;
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kBufCols + g * N1);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const size_t ovox = ((size_t)z * OY + (2 * (y0 + row) + (t >> 1))) * OX + (2 * (x0 + col) + (t & 1));
+#pragma unroll
+          for (int cb = 0; cb < COUT / 16; ++cb) {
+            uint32_t r[16];
+            tc_ld16(taddr + t * COUT + cb * 16, r);
+            float v[16];
+            if (SPLIT) {
+              uint32_t r2[16];
+              tc_ld16(taddr + N2 + t * COUT + cb * 16, r2);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+            } else {
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + cb * 16 + i);
+            if (valid) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                float hi[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
+                const size_t plane = ((size_t)b * (COUT / 8) + cb * 2 + h) * P;
+                out16[plane * oplane_vox + ovox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
+                                                              pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+                if (SPLIT) {
+                  float lo[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
+                  out16[(plane + 1) * oplane_vox + ovox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
+                                                                      pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(8 + buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Host side: tensor maps, tile selection, launch
 // ------------------------------------------------------------------------------------------
@@ -587,6 +771,36 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
   launch_tile<CIN, COUT, SPLIT>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
 }
 
+
+template <int CIN, int COUT, bool SPLIT>
+void launch_convT_cfg(const __half* in, const PackedConv& w, __half* out, int nb, Int3 sz, cudaStream_t s) {
+  constexpr int P = SPLIT ? 2 : 1;
+  constexpr int NPL = P * CIN / 8, N1 = 4 * P * COUT, WBYTES = N1 * CIN * 2;
+  UmmaConvTParams p{};
+  p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
+  const int maxg = kBufCols / N1;
+  // tile: XT = X (<= 128, one contiguous TMA row), TY rows so that TY * XT = G * 128 positions
+  p.XT = std::min(sz.x + (sz.x & 1), 128);
+  p.TY = std::max(1, (maxg * 128) / p.XT);
+  p.TY = std::min(p.TY, sz.y);
+  p.G = ceil_div(p.TY * p.XT, 128);
+  while (p.G > maxg && p.TY > 1) { --p.TY; p.G = ceil_div(p.TY * p.XT, 128); }
+  if (p.G > maxg) throw std::runtime_error("convT_umma: tile does not fit TMEM");
+  p.tiles_x = ceil_div(sz.x, p.XT);
+  p.tiles_y = ceil_div(sz.y, p.TY);
+  p.planes = CIN / 8;
+  p.plane_stride = (uint32_t)(p.TY * p.XT * 16);
+  p.slot_stride = (uint32_t)((NPL * (size_t)p.plane_stride + 127) / 128 * 128);
+  p.wpacked = w.w; p.bias = w.bias; p.out = out;
+  const size_t smem = (size_t)kRing * p.slot_stride + WBYTES + 128 + kTailPad + 128;
+  if (smem > (size_t)kMaxSmem) throw std::runtime_error("convT_umma: shared memory exceeded");
+  const CUtensorMap mapA = make_map(in, nb * p.planes * P, sz, p.XT, p.TY, p.planes * P, /*wide=*/false);
+  auto kern = convT_umma_kernel<CIN, COUT, SPLIT>;
+  CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, p);
+  CFB_LAUNCH_CHECK();
+}
+
 template <bool SPLIT>
 void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb, Int3 sz,
               bool relu, cudaStream_t s) {
@@ -627,6 +841,40 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
             const __half val = n < cout ? hi : __float2half_rn(wv - __half2float(hi));
             buf[((size_t)t * KG + g) * block + ((size_t)kc * NB + n) * 8 + e] = val;
           }
+  out.cin = cin; out.cout = cout; out.parts = parts;
+  out.tuned = std::make_shared<std::map<uint64_t, ConvTile>>();
+  out.bytes = buf.size() * sizeof(__half);
+  CFB_CUDA(cudaMalloc(&out.w, out.bytes));
+  CFB_CUDA(cudaMemcpy(out.w, buf.data(), out.bytes, cudaMemcpyHostToDevice));
+  CFB_CUDA(cudaMalloc(&out.bias, cout * sizeof(float)));
+  CFB_CUDA(cudaMemcpy(out.bias, h_bias, cout * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int nb, Int3 in_size, cudaStream_t s) {
+  const bool split = w.parts == 2;
+#define CFB_CASE(CI, CO)                                                                     \
+  if (w.cin == CI && w.cout == CO) {                                                         \
+    if (split) return launch_convT_cfg<CI, CO, true>(in, w, out, nb, in_size, s);            \
+    return launch_convT_cfg<CI, CO, false>(in, w, out, nb, in_size, s);                      \
+  }
+  CFB_CASE(64, 32) CFB_CASE(32, 16)
+#undef CFB_CASE
+  throw std::runtime_error("convT_umma: unsupported channel configuration");
+}
+
+void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out) {
+  free_packed(out);
+  const int N1 = 4 * parts * cout, N2 = 4 * cout;
+  std::vector<__half> buf((size_t)N1 * cin);
+  for (int kc = 0; kc < cin / 8; ++kc)
+    for (int n = 0; n < N1; ++n)
+      for (int e = 0; e < 8; ++e) {
+        const int ci = kc * 8 + e;
+        const int nn = n % N2, t = nn / cout, co = nn % cout;
+        const float wv = h_w[((size_t)ci * cout + co) * 4 + t];  // (cin, cout, 1, 2, 2)
+        const __half hi = __float2half_rn(wv);
+        buf[((size_t)kc * N1 + n) * 8 + e] = n < N2 ? hi : __float2half_rn(wv - __half2float(hi));
+      }
   out.cin = cin; out.cout = cout; out.parts = parts;
   out.tuned = std::make_shared<std::map<uint64_t, ConvTile>>();
   out.bytes = buf.size() * sizeof(__half);

@@ -46,6 +46,11 @@ void free_packed(PackedConv& p);
 void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out,
                        int nb, Int3 size, bool relu, cudaStream_t s);
 
+// ConvTranspose kernel = stride = (1,2,2) on tcgen05 (GEMM over input voxels + scatter epilogue).
+// h_w: (cin, cout, 1, 2, 2) fp32.  in: CP8 (nb, cin) of size in_size; out: CP8 (nb, cout) of (Z, 2Y, 2X).
+void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out);
+void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int nb, Int3 in_size, cudaStream_t s);
+
 // Layout conversion (tests / debug): planar fp32 (nb, C, Z,Y,X) <-> CP8.
 void launch_planar_to_cp8(const float* in, __half* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
 void launch_cp8_to_planar(const __half* in, float* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
@@ -62,6 +67,13 @@ void launch_maxpool_cp8(const __half* in, __half* out, int channels, int parts, 
 // ConvTranspose kernel=stride=(1,2,2), fp32 math on CUDA cores.  w: (cin, cout, 1,2,2) fp32.
 void launch_convT_cp8(const __half* in, const float* w, const float* bias, __half* out, int cin, int cout,
                       int parts, int nb, Int3 in_size, cudaStream_t s);
+// Fused network tail (reference patch/pytorch.py:105-113 + chunk/base.py:792-807): 1x1x1 head +
+// sigmoid on the last CP8 activation, crop, x bump mask, accumulate into the output chunk with
+// red.global.add -- the raw network output never touches HBM.
+void launch_head_blend_cp8(const __half* in, const float* w, const float* bias, int cin, int cnet, int parts, Int3 in_patch,
+                           Int3 out_patch, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out,
+                           int channels, Int3 out_size, cudaStream_t s);
+
 // 1x1x1 head + sigmoid -> planar fp32 (nb, cout, Z,Y,X).
 void launch_head_sigmoid_cp8(const __half* in, const float* w, const float* bias, float* out, int cin, int cout,
                              int parts, int nb, Int3 size, cudaStream_t s);

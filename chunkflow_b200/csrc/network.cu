@@ -1,6 +1,8 @@
 // Device-side 3-level U-Net: weight packing, workspace and layer dispatch.
 #include "network.cuh"
 
+#include <cstdlib>
+
 #include "chunkflow_b200.h"
 #include "kernels_memory.cuh"
 #include "kernels_simt.cuh"
@@ -108,6 +110,8 @@ bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int 
     CFB_CUDA(cudaMemcpy(L.bias, bi->second.data(), bi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (umma() && sp.taps == 27 && sp.cin >= 16)
       pack_conv3_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
+    if (umma() && sp.taps == 4)
+      pack_convT_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
     layers_[sp.name] = L;
   }
   if (num_output_channels > cnet_) { err = "the network produces fewer channels than num_output_channels"; return false; }
@@ -186,7 +190,8 @@ int Network::forward(int nb, cudaStream_t s) {
   return 15;
 }
 
-int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s) {
+int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s,
+                         bool with_head) {
   const Int3 s0 = patch_, s1{patch_.z, patch_.y / 2, patch_.x / 2}, s2{patch_.z, patch_.y / 4, patch_.x / 4};
   const int P = parts();
   {
@@ -209,19 +214,25 @@ int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPo
   prof_begin("pool1", s); launch_maxpool_cp8(h_e1_, h_p1_, 32, P, nb, s1, s); prof_end(s);
   conv("enc2.0", h_p1_, 32, nullptr, 0, h_e2a_, s2);
   conv("enc2.2", h_e2a_, 64, nullptr, 0, h_e2_, s2);
-  { const ConvLayer& L = layers_.at("up1"); prof_begin("up1", s); launch_convT_cp8(h_e2_, L.w, L.bias, h_u1_, 64, 32, P, nb, s2, s); prof_end(s); }
+  const bool simt_up = getenv("CFB_SIMT_CONVT") != nullptr;
+  { const ConvLayer& L = layers_.at("up1"); prof_begin("up1", s);
+    if (simt_up) launch_convT_cp8(h_e2_, L.w, L.bias, h_u1_, 64, 32, P, nb, s2, s); else launch_convT_umma(h_e2_, L.packed, h_u1_, nb, s2, s);
+    prof_end(s); }
   conv("dec1.0", h_u1_, 32, h_e1_, 32, h_d1a_, s1);  // torch.cat([up1, enc1])
   conv("dec1.2", h_d1a_, 32, nullptr, 0, h_d1_, s1);
-  { const ConvLayer& L = layers_.at("up0"); prof_begin("up0", s); launch_convT_cp8(h_d1_, L.w, L.bias, h_u0_, 32, 16, P, nb, s1, s); prof_end(s); }
+  { const ConvLayer& L = layers_.at("up0"); prof_begin("up0", s);
+    if (simt_up) launch_convT_cp8(h_d1_, L.w, L.bias, h_u0_, 32, 16, P, nb, s1, s); else launch_convT_umma(h_d1_, L.packed, h_u0_, nb, s1, s);
+    prof_end(s); }
   conv("dec0.0", h_u0_, 16, h_e0_, 16, h_d0a_, s0);  // torch.cat([up0, enc0])
   conv("dec0.2", h_d0a_, 16, nullptr, 0, h_d0_, s0);
+  if (!with_head) return 14;  // whole-chunk path: the head is fused into the blend kernel
   { const ConvLayer& L = layers_.at("head"); prof_begin("head", s); launch_head_sigmoid_cp8(h_d0_, L.w, L.bias, net_out_, 16, cnet_, P, nb, s0, s); prof_end(s); }
   return 15;
 }
 
 int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s) {
   if (nb > batch_) throw std::invalid_argument("batch larger than configured");
-  if (umma()) return forward_cp8(chunk, in_dtype, cs, patches, nb, s);
+  if (umma()) return forward_cp8(chunk, in_dtype, cs, patches, nb, s, /*with_head=*/false);
   prof_begin("extract", s);
   launch_extract_patches(chunk, in_dtype, cs, patches, nb, patch_, buf_in_, s);
   prof_end(s);
@@ -231,12 +242,19 @@ int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const 
 int Network::forward_from_host_patches(const float* h_patches, int nb, cudaStream_t s) {
   if (nb > batch_) throw std::invalid_argument("batch larger than configured");
   CFB_CUDA(cudaMemcpyAsync(buf_in_, h_patches, (size_t)nb * vol(patch_) * sizeof(float), cudaMemcpyHostToDevice, s));
-  if (umma()) return forward_cp8(nullptr, 0, Int3{0, 0, 0}, nullptr, nb, s);
+  if (umma()) return forward_cp8(nullptr, 0, Int3{0, 0, 0}, nullptr, nb, s, /*with_head=*/true);
   return forward(nb, s);
 }
 
 int Network::blend(Int3 op, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out, int channels,
                    Int3 out_size, cudaStream_t s) {
+  if (umma()) {
+    const ConvLayer& L = layers_.at("head");
+    prof_begin("head+blend", s);
+    launch_head_blend_cp8(h_d0_, L.w, L.bias, 16, cnet_, parts(), patch_, op, crop, mask, patches, nb, out, channels, out_size, s);
+    prof_end(s);
+    return 1;
+  }
   prof_begin("blend", s);
   launch_blend_patches(net_out_, cnet_, patch_, op, crop, mask, patches, nb, out, channels, out_size, 1.0f, s);
   prof_end(s);

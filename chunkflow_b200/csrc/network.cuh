@@ -48,7 +48,8 @@ class Network {
   void allocate();
   int forward(int nb, cudaStream_t s);  // from buf_in_ (fp32 SIMT path)
   // tcgen05 path: chunk != nullptr -> first layer reads the chunk, else the staged fp32 patches in buf_in_
-  int forward_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, cudaStream_t s);
+  int forward_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, cudaStream_t s,
+                  bool with_head);
   bool umma() const { return precision_ != 0; }
   int parts() const { return precision_ == 1 ? 2 : 1; }
 

@@ -268,3 +268,49 @@ def test_large_chunk_properties():
     assert np.abs(a[0] - a[2]).max() <= BLEND_ATOL
     b = inf(Chunk(img)).array
     assert np.abs(a - b).max() <= BLEND_ATOL
+
+
+def test_cli_readme_example(golden):
+    """README config #1 through the command line: create-chunk 64x256x256 -> inference (b200)."""
+    from click.testing import CliRunner
+    from chunkflow_b200.flow import cli
+    res = CliRunner().invoke(cli.main, [
+        "create-chunk", "--size", "40", "256", "256",
+        "inference", "--input-patch-size", "20", "256", "256", "--output-patch-overlap", "4", "64", "64",
+        "--num-output-channels", "3", "--framework", "b200", "--batch-size", "2", "--mask-output-chunk"],
+        standalone_mode=False)
+    assert res.exception is None, res.output
+    task = res.return_value[0]
+    out = task["chunk"]
+    assert out.shape == (3, 40, 256, 256) and 0 < out.array.min() and out.array.max() < 1
+    assert "inference" in task["log"]["timer"] and "B200" in task["log"]["compute_device"]
+
+
+def test_slab_entry_point_matches_whole_chunk():
+    """cfb_infer_slab_device + cfb_normalize_device (the per-rank half of BASELINE config #5): two z-slabs run
+    one after the other on one GPU, halo planes added on the host, equal the whole-chunk result."""
+    import torch
+    from chunkflow_b200 import distributed as D
+    rng = np.random.default_rng(23)
+    img = rng.integers(1, 255, size=(27, 40, 44), dtype=np.uint8)
+    inf = _inferencer(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=2,
+                      batch_size=4, framework="identity")
+    whole = inf(Chunk(img)).array
+    eng = inf.engine
+    slabs = D.plan_z_slabs(27, 8, 2, 2)
+    acc = np.zeros((2, 27, 40, 44), np.float32)
+    wsum = np.zeros((27, 40, 44), np.float32)
+    for s in slabs:
+        sub = np.ascontiguousarray(img[s.z0:s.z1])
+        d_in = torch.from_numpy(sub).cuda()
+        shape = eng.output_shape(sub.shape)
+        part = torch.empty(shape, dtype=torch.float32, device="cuda")
+        w = torch.empty(shape[1:], dtype=torch.float32, device="cuda")
+        eng.infer_slab_device(d_in.data_ptr(), sub.dtype, sub.shape, 0, s.row_end - s.row_begin, part.data_ptr(), w.data_ptr())
+        torch.cuda.synchronize()
+        acc[:, s.z0:s.z1] += part.cpu().numpy()
+        wsum[s.z0:s.z1] += w.cpu().numpy()
+    d_acc, d_w = torch.from_numpy(acc).cuda(), torch.from_numpy(wsum).cuda()
+    eng.normalize_device(d_acc.data_ptr(), d_w.data_ptr(), d_acc.shape)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(d_acc.cpu().numpy(), whole, rtol=0, atol=BLEND_ATOL)

@@ -112,3 +112,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_cli_accepts_every_reference_inference_flag():
+    """The `inference` command keeps the reference's option surface (flow/flow.py:1853-1893)."""
+    from chunkflow_b200.flow.cli import inference, create_chunk
+    opts = {o for p in inference.params for o in p.opts + p.secondary_opts}
+    for flag in ["--name", "--convnet-model", "-m", "--convnet-weight-path", "-w", "--input-patch-size", "-s",
+                 "--output-patch-size", "-z", "--output-patch-overlap", "-v", "--output-crop-margin", "--patch-num", "-n",
+                 "--num-input-channels", "--num-output-channels", "-c", "--dtype", "-d", "--framework", "-f",
+                 "--batch-size", "-b", "--bump", "--mask-output-chunk", "--no-mask-output-chunk",
+                 "--mask-myelin-threshold", "-y", "--augment", "--no-augment", "--input-chunk-name", "-i",
+                 "--output-chunk-name", "-o"]:
+        assert flag in opts, flag
+    fw = next(p for p in inference.params if p.name == "framework")
+    assert {"universal", "identity", "pytorch", "b200"} <= set(fw.type.choices)
+    assert next(p for p in inference.params if p.name == "mask_output_chunk").default is False   # CLI default (ctor: True)
+    assert next(p for p in inference.params if p.name == "output_patch_overlap").default == (4, 64, 64)
+    assert "--size" in {o for p in create_chunk.params for o in p.opts}

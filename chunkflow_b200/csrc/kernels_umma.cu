@@ -130,6 +130,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor), 64 bits:
 //   [0,14)  start address >> 4      [16,30) leading byte offset >> 4 (between the two 8-element K chunks)
@@ -159,6 +167,8 @@ struct UmmaConvParams {
   int bstages;    // weight block stages in shared memory
   int bresident;  // 1: all 27*KG blocks stay resident (loaded once per CTA), 0: streamed through a ring
   int wide_map;   // 1: 5-D tensor map with the 16-byte record as inner dimension, 0: 4-D map over 8-byte elements
+  int T;          // z-stacked kernel: output planes per job
+  const __half* wpacked_zs;  // z-stacked weight blocks
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
@@ -407,6 +417,270 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// z-stacked variant: one activation-tile read serves the three z-taps.
+//
+// The plain kernel re-reads the 4 KB activation tile of a position run for each of the 27 taps.
+// Here a job covers T consecutive OUTPUT planes of the column; INPUT plane q is multiplied, for each
+// (dy, dx), by the weight rows of dz = 2, 1, 0 stacked along N (one tcgen05.mma, N = 3 * NB), whose
+// column groups land in the accumulators of output planes q-1, q, q+1 -- the same TMEM lanes
+// (positions), adjacent column ranges.  A tile is therefore read 9 * (T+2) / T times per output
+// plane instead of 27, and N per instruction triples (tensor pipe duty cycle up).  Accumulators are
+// zeroed by the epilogue after draining (tcgen05.st), so every MMA accumulates.
+// Weight block (dy, dx, kg): [KB/8][3 * NB rows: dz=2 | dz=1 | dz=0, each (hi COUT | lo COUT)][8].
+// In split mode the a_lo pass uses the same window (it adds the exact a_lo * w_lo term as well).
+// ------------------------------------------------------------------------------------------
+template <int CIN, int COUT, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const UmmaConvParams p) {
+  using Cfg = ConvCfg<CIN, COUT, SPLIT>;
+  constexpr int P = Cfg::P;
+  constexpr int NB = Cfg::NB;
+  constexpr int BSTAGE = 3 * Cfg::BSTAGE;  // three dz row groups per block
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tx = blockIdx.x % p.tiles_x;
+  const int ty = (blockIdx.x / p.tiles_x) % p.tiles_y;
+  const int b = blockIdx.x / (p.tiles_x * p.tiles_y);
+  const int x0 = tx * p.XT, y0 = ty * p.TY;
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kRing * p.slot_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.bstages * BSTAGE);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int kBF = 10, kBE = 10 + kMaxBStages, kAccF = 6, kAccE = 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBE + kMaxBStages);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+    for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), 1); mbar_init(BAR(kAccE + i), 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int Z = p.Z, T = p.T;
+  const int njobs = (Z + T - 1) / T;
+
+  if (warp == 0) {
+    // ---------------- A producer: for every job its input planes max(z0-1,0) .. min(z0+T, Z-1) ----------------
+    if (elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
+      const int plane_a0 = b * p.planes_a * P, plane_b0 = b * p.planes_b * P;
+      int slot = 0, ld = 0;
+      uint32_t prev_parity = 1;
+      for (int j = 0; j < njobs; ++j) {
+        const int z0 = j * T, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+        for (int q = qlo; q <= qhi; ++q, ++ld) {
+          if (ld >= kRing) mbar_wait(BAR(3 + slot), prev_parity);
+          mbar_expect_tx(BAR(slot), tx_bytes);
+          const uint32_t dst = smem_u32(sA + (size_t)slot * p.slot_stride);
+          const uint32_t dst_b = dst + (uint32_t)(p.planes_a * P) * p.plane_stride;
+          if (p.wide_map) {
+            tma_load_5d(dst, &mapA, BAR(slot), 0, x0 - 1, y0 - 1, q, plane_a0);
+            if (p.planes_b > 0) tma_load_5d(dst_b, &mapB, BAR(slot), 0, x0 - 1, y0 - 1, q, plane_b0);
+          } else {
+            tma_load_4d(dst, &mapA, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_a0);
+            if (p.planes_b > 0) tma_load_4d(dst_b, &mapB, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_b0);
+          }
+          if (++slot == kRing) { slot = 0; prev_parity ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- B producer: 9 * KG blocks per input plane ----------------
+    if (elect_one()) {
+      const uint32_t per_plane = 9u * Cfg::KG;
+      const uint32_t nbs = (uint32_t)p.bstages;
+      uint32_t planes = 0;
+      for (int j = 0; j < njobs; ++j) planes += (uint32_t)(min(j * T + T, Z - 1) - max(j * T - 1, 0) + 1);
+      const uint32_t total = p.bresident ? per_plane : planes * per_plane;
+      uint32_t st = 0, blk = 0, prev_parity = 1;
+      for (uint32_t i = 0; i < total; ++i) {
+        if (i >= nbs) mbar_wait(BAR(kBE + st), prev_parity);
+        mbar_expect_tx(BAR(kBF + st), BSTAGE);
+        bulk_load(smem_u32(sB + st * BSTAGE), reinterpret_cast<const uint8_t*>(p.wpacked_zs) + (size_t)blk * BSTAGE,
+                  BSTAGE, BAR(kBF + st));
+        if (++st == nbs) { st = 0; prev_parity ^= 1; }
+        if (++blk == per_plane) blk = 0;
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer ----------------
+    if (elect_one()) {
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
+      const uint32_t plane16 = p.plane_stride >> 4;
+      const uint32_t a_lbo = (P * plane16) << 16;
+      constexpr uint32_t b_lbo = (uint32_t)(3 * NB) << 16;
+      const uint32_t sA16 = smem_u32(sA) >> 4, slot16 = p.slot_stride >> 4;
+      const uint32_t sB16 = smem_u32(sB) >> 4;
+      const uint32_t pitch = (uint32_t)p.pitch, tstride = (uint32_t)p.tile_stride, G = (uint32_t)p.G;
+      const uint32_t kstep16 = 2u * P * plane16;
+      const bool resident = p.bresident != 0;
+      const uint32_t nbs = (uint32_t)p.bstages;
+      auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+      uint32_t ring_st = 0, ring_parity = 0;
+      uint32_t slot = 0, sparity = 0;
+      bool first_plane = true;
+      for (int j = 0; j < njobs; ++j) {
+        const uint32_t buf = (uint32_t)j & 1u;
+        mbar_wait(BAR(kAccE + buf), (uint32_t)(j >> 1) & 1u);  // zeroed by the epilogue (initially and after draining)
+        tc_fence_after();
+        const int z0 = j * T, z1 = min(z0 + T, Z), qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+        const uint32_t dbuf = tmem_base + buf * kBufCols;
+        for (int q = qlo; q <= qhi; ++q) {
+          mbar_wait(BAR(slot), sparity);
+          tc_fence_after();
+          const int plo = max(q - 1, z0), phi = min(q + 1, z1 - 1);
+          const uint32_t ng = (uint32_t)(phi - plo + 1);
+          const uint32_t row0 = (uint32_t)(2 - (q - plo + 1)) * NB;  // first weight row group: dz = q - plo + 1
+          const uint32_t idesc = make_idesc((int)(ng * NB));
+          const uint32_t dcol0 = dbuf + (uint32_t)(plo - z0) * NB;
+          uint32_t a_row = a_lbo | (sA16 + slot * slot16);
+          uint32_t blk = 0;
+          for (int dy = 0; dy < 3; ++dy, a_row += pitch) {
+            for (uint32_t dx = 0; dx < 3; ++dx) {
+              const uint32_t a_tap = a_row + dx;
+              for (int kg = 0; kg < Cfg::KG; ++kg) {
+                uint32_t b16;
+                if (resident) {
+                  if (first_plane) { mbar_wait(BAR(kBF + blk), 0); tc_fence_after(); }
+                  b16 = sB16 + blk * (BSTAGE >> 4);
+                  ++blk;
+                } else {
+                  mbar_wait(BAR(kBF + ring_st), ring_parity);
+                  tc_fence_after();
+                  b16 = sB16 + ring_st * (BSTAGE >> 4);
+                }
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KS; ++ks) {
+                  const uint64_t bdesc = desc(b_lbo | (b16 + (uint32_t)ks * 2u * (3 * NB) + row0));
+                  uint32_t a_lo = a_tap + (uint32_t)(kg * Cfg::KS + ks) * kstep16;
+                  uint32_t d = dcol0;
+                  for (uint32_t g = 0; g < G; ++g, a_lo += tstride, d += (uint32_t)T * NB) {
+                    tc_mma_f16(d, desc(a_lo), bdesc, idesc, 1u);
+                    if (SPLIT) tc_mma_f16(d, desc(a_lo + plane16), bdesc, idesc, 1u);
+                  }
+                }
+                if (!resident) {
+                  tc_commit(BAR(kBE + ring_st));
+                  if (++ring_st == nbs) { ring_st = 0; ring_parity ^= 1; }
+                }
+              }
+            }
+          }
+          first_plane = false;
+          tc_commit(BAR(3 + slot));  // this input plane is consumed
+          if (++slot == kRing) { slot = 0; sparity ^= 1; }
+        }
+        tc_commit(BAR(kAccF + buf));
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    // zero both accumulator buffers once (TMEM is not cleared by allocation)
+    {
+      const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 512; c += 16) tc_st16(tmem_base + lane_base + c, zero);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR(kAccE + 0));
+      mbar_arrive(BAR(kAccE + 1));
+    }
+    const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
+    const size_t plane_vox = (size_t)p.Z * p.Y * p.X;
+    const float inv_pitch = 1.0f / (float)p.pitch;
+    uint4* out16 = reinterpret_cast<uint4*>(p.out);
+    for (int j = 0; j < njobs; ++j) {
+      const int buf = j & 1;
+      const int z0 = j * T, z1 = min(z0 + T, Z);
+      mbar_wait(BAR(kAccF + buf), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      for (int g = 0; g < p.G; ++g) {
+        const int m = wq * 32 + lane;
+        const int qpos = g * p.tile_stride + m;
+        const int row = __float2int_rd(((float)qpos + 0.5f) * inv_pitch), col = qpos - row * p.pitch;
+        const bool valid = row < ty_valid && col < xt_valid;
+        for (int pz = z0; pz < z1; ++pz) {
+          const size_t vox = ((size_t)pz * p.Y + (y0 + row)) * p.X + (x0 + col);
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kBufCols + (g * T + (pz - z0)) * NB);
+#pragma unroll
+          for (int cb = 0; cb < COUT / 16; ++cb) {
+            uint32_t r[16];
+            tc_ld16(taddr + cb * 16, r);
+            float v[16];
+            if (SPLIT) {
+              uint32_t r2[16];
+              tc_ld16(taddr + COUT + cb * 16, r2);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+            } else {
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] += __ldg(p.bias + cb * 16 + i);
+              if (p.relu) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (valid) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int chunk = cb * 2 + h;
+                float hi[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
+                const size_t plane = ((size_t)b * (COUT / 8) + chunk) * P;
+                out16[plane * plane_vox + vox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
+                                                            pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+                if (SPLIT) {
+                  float lo[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
+                  out16[(plane + 1) * plane_vox + vox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
+                                                                    pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+                }
+              }
+            }
+          }
+          // clear the accumulator for its next use
+          {
+            const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < NB; c += 16) tc_st16(taddr + c, zero);
+          }
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR(kAccE + buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // Transposed convolution kernel = stride = (1,2,2) on tcgen05: a plain GEMM per input voxel,
@@ -674,6 +948,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
       if (bs >= all_blocks) bs = all_blocks;
       if (bs < 3) continue;
       ConvTile t;
+      t.T = 0;
       t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
       const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
       const double lookahead = t.resident ? 1e9 : (double)(bs - 1) * G * Cfg::KS * Cfg::P;
@@ -684,6 +959,43 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
                (lookahead >= 96 ? 0.0 : 0.4 * (96 - lookahead) / 96);
       out.push_back(t);
     }
+    // z-stacked variants: T output planes per job, accumulators (G * T * NB columns) per TMEM buffer
+    if (3 * Cfg::NB <= 256 && !getenv("CFB_NO_ZSTACK")) {
+      for (int T : {2, 4, 8}) {
+        if (T > sz.z && T != 2) continue;
+        for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
+          const size_t plane = (size_t)(tyc + 2) * pitch * 16;
+          const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
+          const int G = aligned ? tyc : ceil_div(tyc * pitch, 128);
+          if (G * T * Cfg::NB > kBufCols || slot >= (1u << 18)) continue;
+          const size_t fixed = (size_t)kBarBytes + kTailPad + 128;
+          if ((size_t)kRing * slot + fixed >= (size_t)kMaxSmem) continue;
+          const size_t room = (size_t)kMaxSmem - (size_t)kRing * slot - fixed;
+          const int all_blocks = 9 * Cfg::KG;
+          const int bstage = 3 * Cfg::BSTAGE;
+          int bs = (int)std::min<size_t>(room / bstage, kMaxBStages);
+          if (bs >= all_blocks) bs = all_blocks;
+          if (bs < 2) continue;
+          ConvTile t;
+          t.T = T; t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
+          const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
+          const double lookahead = t.resident ? 1e9 : (double)(bs - 1) * G * Cfg::KS * Cfg::P * 3;
+          const int ctas = nb * ceil_div(sz.x, XT) * ceil_div(sz.y, tyc);
+          const double waves = (double)ctas / sm_count;
+          const double quant = std::ceil(waves) / waves;
+          // one tile read serves three z-taps: (T + 2) / (3 T) of the plain kernel's operand traffic
+          t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T) + 0.25)) * quant +
+                   (lookahead >= 96 ? 0.0 : 0.4 * (96 - lookahead) / 96);
+          out.push_back(t);
+        }
+      }
+    }
+  }
+  if (const char* force = getenv("CFB_FORCE_ZSTACK")) {  // tests: exercise one kernel variant only
+    const int T = atoi(force);
+    std::vector<ConvTile> only;
+    for (const ConvTile& t : out) if (t.T == T) only.push_back(t);
+    if (!only.empty()) out.swap(only);
   }
   std::sort(out.begin(), out.end(), [](const ConvTile& a, const ConvTile& b) { return a.cost < b.cost; });
   return out;
@@ -709,10 +1021,23 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   p.plane_stride = (uint32_t)((p.TY + 2) * p.pitch * 16);
   p.slot_stride = (uint32_t)((Cfg::NPL * (size_t)p.plane_stride + 127) / 128 * 128);
   p.planes_a = ca / 8; p.planes_b = cb / 8;
-  p.wpacked = w.w; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
-  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * Cfg::BSTAGE + kBarBytes + kTailPad + 128;
+  p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
+  p.T = t.T;
+  const size_t bstage = t.T ? 3 * (size_t)Cfg::BSTAGE : (size_t)Cfg::BSTAGE;
+  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + kBarBytes + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
+  if (t.T) {
+    if constexpr (3 * Cfg::NB <= 256) {
+      auto zk = conv3_zs_umma_kernel<CIN, COUT, SPLIT>;
+      CFB_CUDA(cudaFuncSetAttribute(zk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      zk<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, mapB, p);
+      CFB_LAUNCH_CHECK();
+      return;
+    } else {
+      throw std::runtime_error("z-stacked kernel needs 3 * NB <= 256");
+    }
+  }
   auto kern = conv3_umma_kernel<CIN, COUT, SPLIT>;
   CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, mapB, p);
@@ -747,7 +1072,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       CFB_CUDA(cudaEventCreate(&e0));
       CFB_CUDA(cudaEventCreate(&e1));
       float best_ms = 1e30f;
-      const size_t n = std::min<size_t>(cands.size(), 14);
+      const size_t n = std::min<size_t>(cands.size(), 24);
       for (size_t i = 0; i < n; ++i) {
         launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
         CFB_CUDA(cudaEventRecord(e0, s));
@@ -763,8 +1088,8 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       best.cost = best_ms;
     }
     if (getenv("CFB_DEBUG_CFG"))
-      fprintf(stderr, "[cfb] conv3 %d->%d split=%d size=%dx%dx%d nb=%d: XT=%d%s TY=%d bstages=%d resident=%d (%s %.3f)\n",
-              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.XT, best.wide ? "w" : "", best.TY, best.bstages,
+      fprintf(stderr, "[cfb] conv3 %d->%d split=%d size=%dx%dx%d nb=%d: zstack T=%d XT=%d%s TY=%d bstages=%d resident=%d (%s %.3f)\n",
+              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.T, best.XT, best.wide ? "w" : "", best.TY, best.bstages,
               (int)best.resident, tune ? "tuned ms" : "model cost", best.cost);
     it = w.tuned->emplace(key, best).first;
   }
@@ -848,6 +1173,24 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
   CFB_CUDA(cudaMemcpy(out.w, buf.data(), out.bytes, cudaMemcpyHostToDevice));
   CFB_CUDA(cudaMalloc(&out.bias, cout * sizeof(float)));
   CFB_CUDA(cudaMemcpy(out.bias, h_bias, cout * sizeof(float), cudaMemcpyHostToDevice));
+  // z-stacked blocks: (dy, dx, kg): [KB/8][3*NB rows: dz = 2 | 1 | 0][8]
+  std::vector<__half> zs((size_t)27 * KG * block);
+  for (int t9 = 0; t9 < 9; ++t9)
+    for (int g = 0; g < KG; ++g)
+      for (int kc = 0; kc < KB / 8; ++kc)
+        for (int zi = 0; zi < 3; ++zi)
+          for (int n = 0; n < NB; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int dz = 2 - zi, t = dz * 9 + t9;
+              const int ci = g * KB + kc * 8 + e;
+              const int co = n % cout;
+              const float wv = h_w[((size_t)co * cin + ci) * 27 + t];
+              const __half hi = __float2half_rn(wv);
+              const __half val = n < cout ? hi : __float2half_rn(wv - __half2float(hi));
+              zs[((size_t)t9 * KG + g) * (3 * block) + ((size_t)kc * 3 * NB + (size_t)zi * NB + n) * 8 + e] = val;
+            }
+  CFB_CUDA(cudaMalloc(&out.w_zs, zs.size() * sizeof(__half)));
+  CFB_CUDA(cudaMemcpy(out.w_zs, zs.data(), zs.size() * sizeof(__half), cudaMemcpyHostToDevice));
 }
 
 void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int nb, Int3 in_size, cudaStream_t s) {
@@ -886,6 +1229,7 @@ void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout
 
 void free_packed(PackedConv& p) {
   if (p.w) cudaFree(p.w);
+  if (p.w_zs) cudaFree(p.w_zs);
   if (p.bias) cudaFree(p.bias);
   p = PackedConv{};
 }

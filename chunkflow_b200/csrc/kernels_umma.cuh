@@ -26,12 +26,14 @@ namespace cfb {
 // stages, resident weights, TMA map flavour.
 struct ConvTile {
   int XT = 0, TY = 0, bstages = 0;
+  int T = 0;  // > 0: z-stacked kernel with T output planes per job
   bool resident = false, wide = false;
   double cost = 0.0;
 };
 
 struct PackedConv {
-  __half* w = nullptr;  // device
+  __half* w = nullptr;     // device, per-tap blocks
+  __half* w_zs = nullptr;  // device, z-stacked blocks (3x3x3 layers only)
   float* bias = nullptr;
   int cin = 0, cout = 0, parts = 1;
   size_t bytes = 0;

@@ -155,6 +155,17 @@ def test_conv3_layer_tcgen05_split_against_torch(cin, cout, size):
     _conv3_case(_native.PRECISION_F16X3_UMMA, cin, cout, size, 5e-5)
 
 
+@pytest.mark.parametrize("zstack", ["2", "4", "8"])
+@pytest.mark.parametrize("cin,cout,size", [(16, 16, (3, 8, 40)), (16, 16, (9, 16, 70)), (32, 32, (5, 12, 20)), (16, 32, (4, 6, 128)),
+                                           (32, 16, (7, 8, 130)), (64, 32, (4, 16, 16)), (16, 16, (1, 7, 9))])
+def test_conv3_layer_tcgen05_zstacked_kernel(monkeypatch, zstack, cin, cout, size):
+    """The z-stacked kernel variant (T output planes per job, dz taps stacked along N), forced."""
+    monkeypatch.setenv("CFB_FORCE_ZSTACK", zstack)
+    _conv3_case(_native.PRECISION_F16X3_UMMA, cin, cout, size, 5e-5)
+    if cin == 16:
+        _conv3_case(_native.PRECISION_F16_UMMA, cin, cout, size, 1e-2)
+
+
 @pytest.mark.parametrize("cin,cout,size", UMMA_CASES[:4])
 def test_conv3_layer_tcgen05_fp16_against_torch(cin, cout, size):
     # single-pass fp16: 11-bit operands and 11-bit stored outputs on values of magnitude ~5

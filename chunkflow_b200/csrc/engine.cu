@@ -114,6 +114,8 @@ struct cfb_engine {
 
   unsigned int* d_flags = nullptr;  // [0] nonzero flag, [1] max bits
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr;
   void* d_host_in = nullptr; size_t host_in_cap = 0;
   float* d_host_out = nullptr; size_t host_out_cap = 0;
   float* d_plugin_out = nullptr; size_t plugin_out_cap = 0;
@@ -131,6 +133,8 @@ struct cfb_engine {
     cudaFree(d_cover_z_slab); cudaFree(d_host_in); cudaFree(d_host_out); cudaFree(d_plugin_out); cudaFree(d_plugin_in);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (ev_ready) cudaEventDestroy(ev_ready);
   }
 };
 
@@ -217,14 +221,46 @@ void ensure_winv(cfb_engine* e, cudaStream_t s) {
   e->winv_valid = true;
 }
 
+// Progressive download (host variant): output planes are final as soon as every patch z-row that
+// touches them has been blended (rows are processed in ascending z), so they are normalised and
+// copied to the host on a second stream while later rows are still being computed.
+struct Progressive {
+  float* h_out = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ready = nullptr;
+  const float* winv = nullptr;
+  int planes_done = 0;
+};
+
+void flush_planes(cfb_engine* e, Progressive* pg, float* d_out, int z_end, cudaStream_t s) {
+  if (z_end <= pg->planes_done) return;
+  const int C = e->p.num_output_channels;
+  const int64_t plane = (int64_t)e->out_size.y * e->out_size.x, nvox = vol(e->out_size);
+  const int64_t off = (int64_t)pg->planes_done * plane, count = (int64_t)(z_end - pg->planes_done) * plane;
+  launch_normalize(d_out + off, pg->winv ? pg->winv + off : nullptr, true, C, count, e->d_flags + 1, e->d_flags, s, nvox);
+  e->launches++;
+  CFB_CUDA(cudaEventRecord(pg->ready, s));
+  CFB_CUDA(cudaStreamWaitEvent(pg->copy_stream, pg->ready, 0));
+  for (int c = 0; c < C; ++c)
+    CFB_CUDA(cudaMemcpyAsync(pg->h_out + c * nvox + off, d_out + c * nvox + off, (size_t)count * sizeof(float),
+                             cudaMemcpyDeviceToHost, pg->copy_stream));
+  pg->planes_done = z_end;
+}
+
 // Runs the patch loop for patches [first, last) and accumulates into d_out.
 void run_patches(cfb_engine* e, const void* d_in, int in_dtype, int64_t first, int64_t last, float* d_out,
-                 cudaStream_t s) {
+                 cudaStream_t s, Progressive* pg = nullptr) {
   const Int3 cs = e->cached_chunk;
   const int C = e->p.num_output_channels;
   const int B = std::max(1, e->p.batch_size);
+  const int64_t per_row = (int64_t)e->gy.in_start.size() * e->gx.in_start.size();
   for (int64_t i = first; i < last; i += B) {
     const int nb = (int)std::min<int64_t>(B, last - i);
+    if (pg) {
+      // every patch of z-rows < row is launched: planes below the output start of `row` are final
+      const int64_t row = i / per_row;
+      if (row < (int64_t)e->gz.out_start.size()) flush_planes(e, pg, d_out, std::max(0, std::min(e->gz.out_start[row], e->out_size.z)), s);
+    }
     const PatchPos* pp = e->d_patches + i;
     if (e->p.framework == CFB_FRAMEWORK_IDENTITY) {
       launch_identity_blend(d_in, in_dtype, cs, e->ip, e->op, e->pcrop, e->d_mask, pp, nb, d_out, C, e->out_size, s);
@@ -237,7 +273,8 @@ void run_patches(cfb_engine* e, const void* d_in, int in_dtype, int64_t first, i
 }
 
 int infer_impl(cfb_engine* e, const void* d_in, int in_dtype, int64_t cz, int64_t cy, int64_t cx,
-               int64_t zrow_begin, int64_t zrow_end, bool slab, float* d_out, float* d_weight, cudaStream_t s) {
+               int64_t zrow_begin, int64_t zrow_end, bool slab, float* d_out, float* d_weight, cudaStream_t s,
+               Progressive* pg = nullptr) {
   if (in_dtype != CFB_DTYPE_U8 && in_dtype != CFB_DTYPE_F32) throw std::invalid_argument("unsupported input dtype");
   if (e->p.framework == CFB_FRAMEWORK_UNET3L && !e->net.ready()) {
     set_last_error("weights not committed: call cfb_set_weight for every tensor, then cfb_commit_weights");
@@ -259,8 +296,12 @@ int infer_impl(cfb_engine* e, const void* d_in, int in_dtype, int64_t cz, int64_
   } else {
     zrow_begin = 0; zrow_end = nz;
   }
+  if (pg) {
+    if (slab || e->p.has_myelin_threshold) pg = nullptr;  // those need the whole volume before the final pass
+    else if (e->p.mask_output_chunk) { ensure_winv(e, s); pg->winv = e->d_winv; }
+  }
   CFB_CUDA(cudaEventRecord(e->ev[1], s));
-  run_patches(e, d_in, in_dtype, zrow_begin * ny * nx, zrow_end * ny * nx, d_out, s);
+  run_patches(e, d_in, in_dtype, zrow_begin * ny * nx, zrow_end * ny * nx, d_out, s, pg);
   CFB_CUDA(cudaEventRecord(e->ev[2], s));
   if (slab) {
     // partial weight sum of this slab's patches only
@@ -272,6 +313,8 @@ int infer_impl(cfb_engine* e, const void* d_in, int in_dtype, int64_t cz, int64_
     launch_weight_volume(e->d_mask, e->op, e->d_cover_z_slab, e->d_cover_y, e->d_cover_x, e->d_oz0, e->d_oy0,
                          e->d_ox0, e->out_size, d_weight, /*invert=*/false, s);
     e->launches++;
+  } else if (pg) {
+    flush_planes(e, pg, d_out, e->out_size.z, s);  // remaining planes
   } else {
     const float* w = nullptr;
     if (e->p.mask_output_chunk) { ensure_winv(e, s); w = e->d_winv; }
@@ -372,6 +415,8 @@ int cfb_create(const cfb_params* params, cfb_handle* out) {
     CFB_CUDA(cudaMemcpy(e->d_mask, e->h_mask.data(), e->h_mask.size() * sizeof(float), cudaMemcpyHostToDevice));
     CFB_CUDA(cudaMalloc(&e->d_flags, 2 * sizeof(unsigned int)));
     CFB_CUDA(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    CFB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CFB_CUDA(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
     for (auto& ev : e->ev) CFB_CUDA(cudaEventCreate(&ev));
     e->net.configure(p.precision, e->ip, std::max(1, p.batch_size));
     *out = e.release();
@@ -490,12 +535,18 @@ int cfb_infer_chunk_host(cfb_handle h, const void* h_in, int32_t in_dtype, int64
     CFB_CUDA(cudaEventRecord(h->ev[4], s));
     CFB_CUDA(cudaMemcpyAsync(h->d_host_in, h_in, in_bytes, cudaMemcpyHostToDevice, s));
     CFB_CUDA(cudaEventRecord(h->ev[5], s));
-    rc = infer_impl(h, h->d_host_in, in_dtype, cz, cy, cx, 0, 0, false, h->d_host_out, nullptr, s);
-    if (rc != CFB_OK) return rc;
+    Progressive pg;
+    pg.h_out = h_out;
+    pg.copy_stream = h->copy_stream;
+    pg.ready = h->ev_ready;
+    const bool progressive = !h->p.has_myelin_threshold;
+    rc = infer_impl(h, h->d_host_in, in_dtype, cz, cy, cx, 0, 0, false, h->d_host_out, nullptr, s, progressive ? &pg : nullptr);
+    if (rc != CFB_OK) { cudaStreamSynchronize(h->copy_stream); return rc; }
     CFB_CUDA(cudaEventRecord(h->ev[6], s));
-    CFB_CUDA(cudaMemcpyAsync(h_out, h->d_host_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (!progressive) CFB_CUDA(cudaMemcpyAsync(h_out, h->d_host_out, out_bytes, cudaMemcpyDeviceToHost, s));
     CFB_CUDA(cudaEventRecord(h->ev[7], s));
     CFB_CUDA(cudaStreamSynchronize(s));
+    CFB_CUDA(cudaStreamSynchronize(h->copy_stream));
     return CFB_OK;
   });
 }

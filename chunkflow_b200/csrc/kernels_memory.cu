@@ -196,11 +196,13 @@ weight_volume_kernel(const float* __restrict__ mask, Int3 op, const int* __restr
 // ---- normalise -----------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 normalize_kernel(float* __restrict__ out, const float* __restrict__ w, bool w_is_inverse, int channels,
-                 int64_t nvox, unsigned int* __restrict__ max_bits, const unsigned int* __restrict__ nonzero_flag) {
+                 int64_t nvox, int64_t cstride, unsigned int* __restrict__ max_bits,
+                 const unsigned int* __restrict__ nonzero_flag) {
   const bool force_zero = nonzero_flag != nullptr && *nonzero_flag == 0u;
   float vmax = 0.0f;
   const int64_t nq = nvox >> 2;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 && (nvox & 3) == 0;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(w)) & 15) == 0 && (nvox & 3) == 0 &&
+                      (cstride & 3) == 0;
   if (vec_ok) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -210,7 +212,7 @@ normalize_kernel(float* __restrict__ out, const float* __restrict__ w, bool w_is
         if (!w_is_inverse) s = make_float4(__fdiv_rn(1.f, s.x), __fdiv_rn(1.f, s.y), __fdiv_rn(1.f, s.z), __fdiv_rn(1.f, s.w));
       }
       for (int c = 0; c < channels; ++c) {
-        float4* p = reinterpret_cast<float4*>(out + (int64_t)c * nvox) + i;
+        float4* p = reinterpret_cast<float4*>(out + (int64_t)c * cstride) + i;
         float4 v = *p;
         v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
         if (force_zero) v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -224,10 +226,10 @@ normalize_kernel(float* __restrict__ out, const float* __restrict__ w, bool w_is
       float s = 1.f;
       if (w != nullptr) s = w_is_inverse ? w[i] : __fdiv_rn(1.f, w[i]);
       for (int c = 0; c < channels; ++c) {
-        float v = out[(int64_t)c * nvox + i] * s;
+        float v = out[(int64_t)c * cstride + i] * s;
         if (force_zero) v = 0.f;
         vmax = fmaxf(vmax, v);
-        out[(int64_t)c * nvox + i] = v;
+        out[(int64_t)c * cstride + i] = v;
       }
     }
   }
@@ -311,9 +313,10 @@ void launch_weight_volume(const float* mask, Int3 op, const int* cover_z, const 
 }
 
 void launch_normalize(float* out, const float* w, bool w_is_inverse, int channels, int64_t nvox,
-                      unsigned int* max_bits, const unsigned int* nonzero_flag, cudaStream_t s) {
-  normalize_kernel<<<grid_for(nvox / 4 + 1), kThreads, 0, s>>>(out, w, w_is_inverse, channels, nvox, max_bits,
-                                                               nonzero_flag);
+                      unsigned int* max_bits, const unsigned int* nonzero_flag, cudaStream_t s, int64_t channel_stride) {
+  if (channel_stride <= 0) channel_stride = nvox;
+  normalize_kernel<<<grid_for(nvox / 4 + 1), kThreads, 0, s>>>(out, w, w_is_inverse, channels, nvox, channel_stride,
+                                                               max_bits, nonzero_flag);
   CFB_LAUNCH_CHECK();
 }
 

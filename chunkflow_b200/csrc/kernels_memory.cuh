@@ -38,8 +38,11 @@ void launch_weight_volume(const float* mask, Int3 out_patch, const int* cover_z,
 // a12+a13 (reference inferencer.py:460-466): out *= winv (broadcast over channels), and
 // track the maximum into *max_bits (float bits, values are >= 0).  If *zero_flag == 0
 // (all-zero input, reference :387-393) the output is forced to zero.
+// `nvox` voxels per channel starting at `out` / `winv`; channels are `channel_stride` floats apart
+// (0 = nvox), so a z-range of planes of a larger volume can be normalised on its own.
 void launch_normalize(float* out, const float* winv, bool w_is_inverse, int channels, int64_t nvox,
-                      unsigned int* max_bits, const unsigned int* nonzero_flag, cudaStream_t s);
+                      unsigned int* max_bits, const unsigned int* nonzero_flag, cudaStream_t s,
+                      int64_t channel_stride = 0);
 
 // a14 (reference chunk/base.py:685-689): out[c] *= (out[last] < thr) for c < channels-1.
 void launch_myelin_mask(float* out, int channels, int64_t nvox, float threshold, cudaStream_t s);

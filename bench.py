@@ -32,6 +32,7 @@ FLOP_PER_PATCH_VOXEL = 141248
 CONV3_FLOP = {  # per full-resolution patch voxel, 3x3x3 layers only (by kernel class name)
     "enc0.0": 864, "enc0.2": 13824, "enc1.0": 27648 / 4, "enc1.2": 55296 / 4, "enc2.0": 110592 / 16,
     "enc2.2": 221184 / 16, "dec1.0": 110592 / 4, "dec1.2": 55296 / 4, "dec0.0": 27648, "dec0.2": 13824,
+    "dec0.2+head+blend": 13824 + 96,  # last conv with the fused 1x1x1 head + sigmoid + mask + blend epilogue
 }
 
 
@@ -224,7 +225,7 @@ def main():
         pass
     conv_ms = sum(layers[k][0] for k in CONV3_FLOP if k in layers)
     conv_launches = sum(layers[k][1] for k in CONV3_FLOP if k in layers)
-    conv_flop = sum(CONV3_FLOP.values()) * P * int(np.prod(patch))
+    conv_flop = sum(v for k, v in CONV3_FLOP.items() if k in layers) * P * int(np.prod(patch))
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "conv3x3x3 stack (all 10 layers, one kernel class)",

@@ -266,8 +266,7 @@ void run_patches(cfb_engine* e, const void* d_in, int in_dtype, int64_t first, i
       launch_identity_blend(d_in, in_dtype, cs, e->ip, e->op, e->pcrop, e->d_mask, pp, nb, d_out, C, e->out_size, s);
       e->launches++;
     } else {
-      e->launches += e->net.forward_from_chunk(d_in, in_dtype, cs, pp, nb, s);
-      e->launches += e->net.blend(e->op, e->pcrop, e->d_mask, pp, nb, d_out, C, e->out_size, s);
+      e->launches += e->net.forward_and_blend(d_in, in_dtype, cs, pp, nb, e->op, e->pcrop, e->d_mask, d_out, C, e->out_size, s);
     }
   }
 }

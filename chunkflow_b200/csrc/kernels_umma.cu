@@ -153,6 +153,59 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Fused network tail for the last 3x3x3 layer (Cout = 16): 1x1x1 head + sigmoid + crop + bump mask +
+// red.global.add into the output chunk, straight from the fp32 accumulator values.
+struct FusedTail {
+  const float* head_w;   // (channels, 16) first rows of the head weight
+  const float* head_b;   // (channels)
+  const PatchPos* patches;
+  const float* mask;     // (op.z, op.y, op.x)
+  float* out;            // (channels, os.z, os.y, os.x)
+  int channels;
+  Int3 op, crop, os;
+};
+
+template <int COUT, bool SPLIT>
+__device__ __forceinline__ void store_cp8_16(const float (&v)[16], int cb, int b, size_t vox, size_t plane_vox,
+                                             uint4* __restrict__ out16) {
+  constexpr int P = SPLIT ? 2 : 1;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int chunk = cb * 2 + h;
+    float hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
+    const size_t plane = ((size_t)b * (COUT / 8) + chunk) * P;
+    out16[plane * plane_vox + vox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
+                                                pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+    if (SPLIT) {
+      float lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
+      out16[(plane + 1) * plane_vox + vox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
+                                                        pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
+    }
+  }
+}
+
+__device__ __forceinline__ void head_blend_16(const float (&v)[16], const FusedTail& t, const float* __restrict__ s_head,
+                                              const PatchPos& pp, int z, int y, int x) {
+  const int oz = z - t.crop.z, oy = y - t.crop.y, ox = x - t.crop.x;  // coordinates in the cropped output patch
+  if (oz < 0 || oz >= t.op.z || oy < 0 || oy >= t.op.y || ox < 0 || ox >= t.op.x) return;
+  const int gz = pp.oz + oz, gy = pp.oy + oy, gx = pp.ox + ox;
+  if (gz < 0 || gz >= t.os.z || gy < 0 || gy >= t.os.y || gx < 0 || gx >= t.os.x) return;  // clipped by the chunk
+  const float m = __ldg(t.mask + ((size_t)oz * t.op.y + oy) * t.op.x + ox);
+  float* dst = t.out + ((size_t)gz * t.os.y + gy) * t.os.x + gx;
+  const size_t out_vol = (size_t)t.os.z * t.os.y * t.os.x;
+  for (int co = 0; co < t.channels; ++co) {
+    float acc = s_head[t.channels * 16 + co];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(v[k], s_head[co * 16 + k], acc);
+    const float sig = __fdiv_rn(1.0f, 1.0f + expf(-acc));
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)co * out_vol), "f"(sig * m) : "memory");
+  }
+}
+
 struct UmmaConvParams {
   int Z, Y, X;
   int XT, TY, pitch, tile_stride, G;
@@ -169,6 +222,7 @@ struct UmmaConvParams {
   int wide_map;   // 1: 5-D tensor map with the 16-byte record as inner dimension, 0: 4-D map over 8-byte elements
   int T;          // z-stacked kernel: output planes per job
   const __half* wpacked_zs;  // z-stacked weight blocks
+  FusedTail tail;  // used by the TAIL = true instantiations only
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
@@ -176,7 +230,7 @@ constexpr int kMaxBStages = 64; // weight block stages: resident (27 * KG <= 54 
 constexpr int kThreads = 224;  // 7 warps
 constexpr int kTailPad = 2304; // dense M tiles may read up to 129 voxel records past the last plane
 constexpr int kBufCols = 256;  // TMEM columns per accumulator buffer (2 buffers)
-constexpr int kBarBytes = (10 + 2 * 64) * 8 + 16;  // mbarriers + TMEM base slot
+constexpr int kBarBytes = (10 + 2 * 64) * 8 + 16 + 640;  // mbarriers + TMEM base slot + head weights (fused tail)
 
 template <int CIN, int COUT, bool SPLIT>
 struct ConvCfg {
@@ -190,7 +244,7 @@ struct ConvCfg {
   static constexpr int MAXG = kBufCols / NB;
 };
 
-template <int CIN, int COUT, bool SPLIT>
+template <int CIN, int COUT, bool SPLIT, bool TAIL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                   const UmmaConvParams p) {
@@ -215,6 +269,13 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int kBF = 10, kBE = 10 + kMaxBStages, kAccF = 6, kAccE = 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBE + kMaxBStages);
+  float* s_head = reinterpret_cast<float*>(bars + kBE + kMaxBStages + 2);
+  PatchPos pp{};
+  if constexpr (TAIL) {
+    for (int i = threadIdx.x; i < p.tail.channels * 16; i += kThreads) s_head[i] = p.tail.head_w[i];
+    for (int i = threadIdx.x; i < p.tail.channels; i += kThreads) s_head[p.tail.channels * 16 + i] = p.tail.head_b[i];
+    pp = p.tail.patches[b];
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
@@ -384,23 +445,8 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             if (p.relu) v[i] = fmaxf(v[i], 0.f);
           }
           if (valid) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int chunk = cb * 2 + h;
-              float hi[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
-              const size_t plane = ((size_t)b * (COUT / 8) + chunk) * P;
-              out16[plane * plane_vox + vox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
-                                                          pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-              if (SPLIT) {
-                float lo[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
-                out16[(plane + 1) * plane_vox + vox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
-                                                                  pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
-              }
-            }
+            if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, z, y0 + row, x0 + col);
+            else store_cp8_16<COUT, SPLIT>(v, cb, b, vox, plane_vox, out16);
           }
         }
       }
@@ -431,7 +477,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 // Weight block (dy, dx, kg): [KB/8][3 * NB rows: dz=2 | dz=1 | dz=0, each (hi COUT | lo COUT)][8].
 // In split mode the a_lo pass uses the same window (it adds the exact a_lo * w_lo term as well).
 // ------------------------------------------------------------------------------------------
-template <int CIN, int COUT, bool SPLIT>
+template <int CIN, int COUT, bool SPLIT, bool TAIL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const UmmaConvParams p) {
@@ -455,6 +501,13 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int kBF = 10, kBE = 10 + kMaxBStages, kAccF = 6, kAccE = 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kBE + kMaxBStages);
+  float* s_head = reinterpret_cast<float*>(bars + kBE + kMaxBStages + 2);
+  PatchPos pp{};
+  if constexpr (TAIL) {
+    for (int i = threadIdx.x; i < p.tail.channels * 16; i += kThreads) s_head[i] = p.tail.head_w[i];
+    for (int i = threadIdx.x; i < p.tail.channels; i += kThreads) s_head[p.tail.channels * 16 + i] = p.tail.head_b[i];
+    pp = p.tail.patches[b];
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
@@ -641,23 +694,8 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               if (p.relu) v[i] = fmaxf(v[i], 0.f);
             }
             if (valid) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const int chunk = cb * 2 + h;
-                float hi[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
-                const size_t plane = ((size_t)b * (COUT / 8) + chunk) * P;
-                out16[plane * plane_vox + vox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
-                                                            pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-                if (SPLIT) {
-                  float lo[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
-                  out16[(plane + 1) * plane_vox + vox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
-                                                                    pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
-                }
-              }
+              if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, pz, y0 + row, x0 + col);
+              else store_cp8_16<COUT, SPLIT>(v, cb, b, vox, plane_vox, out16);
             }
           }
           // clear the accumulator for its next use
@@ -1003,7 +1041,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
 
 template <int CIN, int COUT, bool SPLIT>
 void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w,
-                 __half* out, int nb, Int3 sz, bool relu, cudaStream_t s) {
+                 __half* out, int nb, Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail = nullptr) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
   UmmaConvParams p{};
   p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
@@ -1027,21 +1065,31 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + kBarBytes + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
+  const int grid = nb * p.tiles_x * p.tiles_y;
+  auto run = [&](auto kern) {
+    CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+    CFB_LAUNCH_CHECK();
+  };
+  if (tail) {
+    if constexpr (CIN == 16 && COUT == 16) {
+      p.tail = *tail;
+      if (t.T) run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, true>);
+      else run(conv3_umma_kernel<CIN, COUT, SPLIT, true>);
+      return;
+    } else {
+      throw std::runtime_error("the fused head+blend tail needs a 16->16 layer");
+    }
+  }
   if (t.T) {
     if constexpr (3 * Cfg::NB <= 256) {
-      auto zk = conv3_zs_umma_kernel<CIN, COUT, SPLIT>;
-      CFB_CUDA(cudaFuncSetAttribute(zk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      zk<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, mapB, p);
-      CFB_LAUNCH_CHECK();
+      run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, false>);
       return;
     } else {
       throw std::runtime_error("z-stacked kernel needs 3 * NB <= 256");
     }
   }
-  auto kern = conv3_umma_kernel<CIN, COUT, SPLIT>;
-  CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, mapB, p);
-  CFB_LAUNCH_CHECK();
+  run(conv3_umma_kernel<CIN, COUT, SPLIT, false>);
 }
 
 int sm_count() {
@@ -1058,7 +1106,7 @@ int sm_count() {
 // tiling computes bit-identical results) and cache the winner in the layer's PackedConv.
 template <int CIN, int COUT, bool SPLIT>
 void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
-                Int3 sz, bool relu, cudaStream_t s) {
+                Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail) {
   const uint64_t key = ((uint64_t)sz.z << 48) ^ ((uint64_t)sz.y << 32) ^ ((uint64_t)sz.x << 16) ^ (uint64_t)nb;
   auto it = w.tuned->find(key);
   if (it == w.tuned->end()) {
@@ -1093,7 +1141,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
               (int)best.resident, tune ? "tuned ms" : "model cost", best.cost);
     it = w.tuned->emplace(key, best).first;
   }
-  launch_tile<CIN, COUT, SPLIT>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+  launch_tile<CIN, COUT, SPLIT>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
 }
 
 
@@ -1128,10 +1176,10 @@ void launch_convT_cfg(const __half* in, const PackedConv& w, __half* out, int nb
 
 template <bool SPLIT>
 void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb, Int3 sz,
-              bool relu, cudaStream_t s) {
+              bool relu, cudaStream_t s, const FusedTail* tail) {
   const int cin = ca + cb, cout = w.cout;
 #define CFB_CASE(CI, CO) \
-  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
   CFB_CASE(16, 16) CFB_CASE(16, 32) CFB_CASE(32, 32) CFB_CASE(32, 64) CFB_CASE(64, 64) CFB_CASE(64, 32) CFB_CASE(32, 16)
 #undef CFB_CASE
   throw std::runtime_error("conv3_umma: unsupported channel configuration " + std::to_string(cin) + "->" + std::to_string(cout));
@@ -1140,10 +1188,16 @@ void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const Pack
 }  // namespace
 
 void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
-                       Int3 sz, bool relu, cudaStream_t s) {
+                       Int3 sz, bool relu, cudaStream_t s, const ConvTail* tail) {
   if (ca % 16 || (cb % 16) || w.cin != ca + cb) throw std::runtime_error("conv3_umma: channel mismatch");
-  if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
-  else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+  FusedTail ft{};
+  if (tail) {
+    if (tail->channels > 8) throw std::runtime_error("fused tail: at most 8 channels");
+    ft.head_w = tail->head_w; ft.head_b = tail->head_b; ft.patches = tail->patches; ft.mask = tail->mask; ft.out = tail->out;
+    ft.channels = tail->channels; ft.op = tail->out_patch; ft.crop = tail->crop; ft.os = tail->out_size;
+  }
+  if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
+  else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -45,8 +45,19 @@ void free_packed(PackedConv& p);
 
 // One 3x3x3 convolution + bias + ReLU on tcgen05.  Input = channel concat of srcA (ca channels)
 // and srcB (cb channels, may be null); all tensors CP8 with `parts` parts.
+// If `tail` is given (16 -> 16 layers only) the epilogue does not store the activation but applies the
+// fused network tail: 1x1x1 head + sigmoid + crop + bump mask + red.global.add into the output chunk.
+struct ConvTail {
+  const float* head_w;      // device, (>= channels, 16)
+  const float* head_b;      // device
+  const PatchPos* patches;  // device, this batch
+  const float* mask;        // device, output patch mask
+  float* out;               // device, (channels, out_size)
+  int channels;
+  Int3 out_patch, crop, out_size;
+};
 void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out,
-                       int nb, Int3 size, bool relu, cudaStream_t s);
+                       int nb, Int3 size, bool relu, cudaStream_t s, const ConvTail* tail = nullptr);
 
 // ConvTranspose kernel = stride = (1,2,2) on tcgen05 (GEMM over input voxels + scatter epilogue).
 // h_w: (cin, cout, 1, 2, 2) fp32.  in: CP8 (nb, cin) of size in_size; out: CP8 (nb, cout) of (Z, 2Y, 2X).

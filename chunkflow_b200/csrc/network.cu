@@ -191,7 +191,7 @@ int Network::forward(int nb, cudaStream_t s) {
 }
 
 int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s,
-                         bool with_head) {
+                         bool with_head, const ConvTail* tail) {
   const Int3 s0 = patch_, s1{patch_.z, patch_.y / 2, patch_.x / 2}, s2{patch_.z, patch_.y / 4, patch_.x / 4};
   const int P = parts();
   {
@@ -224,8 +224,15 @@ int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPo
     if (simt_up) launch_convT_cp8(h_d1_, L.w, L.bias, h_u0_, 32, 16, P, nb, s1, s); else launch_convT_umma(h_d1_, L.packed, h_u0_, nb, s1, s);
     prof_end(s); }
   conv("dec0.0", h_u0_, 16, h_e0_, 16, h_d0a_, s0);  // torch.cat([up0, enc0])
+  if (tail) {  // 3x3x3 conv + ReLU + 1x1x1 head + sigmoid + crop + bump mask + blend in one kernel
+    const ConvLayer& L = layers_.at("dec0.2");
+    prof_begin("dec0.2+head+blend", s);
+    launch_conv3_umma(h_d0a_, 16, nullptr, 0, L.packed, h_d0_, nb, s0, /*relu=*/true, s, tail);
+    prof_end(s);
+    return 14;
+  }
   conv("dec0.2", h_d0a_, 16, nullptr, 0, h_d0_, s0);
-  if (!with_head) return 14;  // whole-chunk path: the head is fused into the blend kernel
+  if (!with_head) return 14;  // the head is fused into the blend kernel
   { const ConvLayer& L = layers_.at("head"); prof_begin("head", s); launch_head_sigmoid_cp8(h_d0_, L.w, L.bias, net_out_, 16, cnet_, P, nb, s0, s); prof_end(s); }
   return 15;
 }
@@ -237,6 +244,18 @@ int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const 
   launch_extract_patches(chunk, in_dtype, cs, patches, nb, patch_, buf_in_, s);
   prof_end(s);
   return 1 + forward(nb, s);
+}
+
+int Network::forward_and_blend(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, Int3 op, Int3 crop,
+                               const float* mask, float* out, int channels, Int3 out_size, cudaStream_t s) {
+  if (nb > batch_) throw std::invalid_argument("batch larger than configured");
+  if (umma() && !getenv("CFB_NO_FUSED_TAIL")) {
+    const ConvLayer& H = layers_.at("head");
+    ConvTail tail{H.w, H.bias, patches, mask, out, channels, op, crop, out_size};
+    return forward_cp8(chunk, in_dtype, cs, patches, nb, s, /*with_head=*/false, &tail);
+  }
+  int n = forward_from_chunk(chunk, in_dtype, cs, patches, nb, s);
+  return n + blend(op, crop, mask, patches, nb, out, channels, out_size, s);
 }
 
 int Network::forward_from_host_patches(const float* h_patches, int nb, cudaStream_t s) {

@@ -31,6 +31,10 @@ class Network {
   int forward_from_chunk(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb,
                          cudaStream_t s);
   int forward_from_host_patches(const float* h_patches, int nb, cudaStream_t s);
+  // Whole-chunk path: extract + network + crop + bump mask + accumulate into the output chunk.  On the tcgen05
+  // path the head and the blend are fused into the epilogue of the last convolution.
+  int forward_and_blend(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, Int3 out_patch,
+                        Int3 crop, const float* mask, float* out, int channels, Int3 out_size, cudaStream_t s);
   // crop + bump mask + accumulate the last forward's outputs into the output chunk.
   int blend(Int3 out_patch, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out,
             int channels, Int3 out_size, cudaStream_t s);
@@ -49,7 +53,7 @@ class Network {
   int forward(int nb, cudaStream_t s);  // from buf_in_ (fp32 SIMT path)
   // tcgen05 path: chunk != nullptr -> first layer reads the chunk, else the staged fp32 patches in buf_in_
   int forward_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, cudaStream_t s,
-                  bool with_head);
+                  bool with_head, const ConvTail* tail = nullptr);
   bool umma() const { return precision_ != 0; }
   int parts() const { return precision_ == 1 ? 2 : 1; }
 

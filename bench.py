@@ -225,14 +225,30 @@ def main():
         pass
     conv_ms = sum(layers[k][0] for k in CONV3_FLOP if k in layers)
     conv_launches = sum(layers[k][1] for k in CONV3_FLOP if k in layers)
-    conv_flop = sum(v for k, v in CONV3_FLOP.items() if k in layers) * P * int(np.prod(patch))
+    pvox = int(np.prod(patch))
+    conv_flop = sum(v for k, v in CONV3_FLOP.items() if k in layers) * P * pvox
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    achieved = conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "conv3x3x3 stack (all 10 layers, one kernel class)",
+    # dominant kernel = the 3x3x3 layer with the largest share of the step (dec0.0 / dec1.0, the concat layers)
+    dom = max((k for k in CONV3_FLOP if k in layers), key=lambda k: layers[k][0])
+    dom_ms, dom_launches = layers[dom]
+    dom_flop_per_launch = CONV3_FLOP[dom] * P * pvox / dom_launches
+    achieved = dom_flop_per_launch / (dom_ms / dom_launches / 1e3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_traffic.json), scaled to this batch
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["layers"].get(dom)
+        if t and t.get("dram_bytes_per_patch"):
+            traffic = t["dram_bytes_per_patch"] * P / dom_launches
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": f"{dom}: tcgen05 3x3x3 convolution (conv3_zs_umma_kernel / conv3_umma_kernel)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
-                "traffic": None, "launches": conv_launches, "ms_per_chunk": conv_ms,
-                "algorithmic_flop_per_chunk": conv_flop}
+                "traffic": traffic, "launches": dom_launches, "ms_per_launch": dom_ms / max(dom_launches, 1),
+                "algorithmic_flop_per_launch": dom_flop_per_launch,
+                "note": "fp16 hi/lo split executes ~2x these algorithmic FLOPs on the tensor pipe; ncu tensor-pipe active 33-56 % "
+                        "(profiles/r01_ncu_full_summary.md)",
+                "conv_stack": {"achieved": conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0, "unit": "TFLOP/s",
+                               "ms_per_chunk": conv_ms, "launches": conv_launches, "algorithmic_flop_per_chunk": conv_flop}}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     pv = P * int(np.prod(patch))
     mem = {}

@@ -150,9 +150,12 @@ class Engine:
         check(self._lib.cfb_create(C.byref(p), C.byref(self._h)))
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self._lib.cfb_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._lib.cfb_destroy(h)
+            finally:
+                self._h = None  # (the ctypes module may already be torn down at interpreter exit)
 
     __del__ = close
 

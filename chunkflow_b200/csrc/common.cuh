@@ -38,7 +38,17 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct PatchPos {
   int iz, iy, ix;  // input patch start inside the chunk
   int oz, oy, ox;  // start of the (cropped) output patch inside the output buffer (may be <0 / clipped)
+  int flags;       // test-time augmentation variant: bit 0 transpose y<->x, bit 1 flip x, bit 2 flip y
 };
+
+// Test-time augmentation (reference transform.py:114-145: transpose, then flip x, then flip y).
+// Maps coordinates (y, x) of the TRANSFORMED patch of size (Y, X) back to the original patch.
+// The same map serves the input read and, being its own inverse chain, the output write-back.
+__host__ __device__ __forceinline__ void tta_map(int flags, int Y, int X, int y, int x, int& sy, int& sx) {
+  const int yy = (flags & 4) ? Y - 1 - y : y;
+  const int xx = (flags & 2) ? X - 1 - x : x;
+  if (flags & 1) { sy = xx; sx = yy; } else { sy = yy; sx = xx; }
+}
 
 // Per-axis coverage table for the weight-volume gather: for every output coordinate the
 // (ascending) list of patch axis-indices that cover it; -1 terminated.

@@ -126,6 +126,9 @@ struct cfb_engine {
   bool timing_valid = false;
   int64_t launches = 0;
 
+  // reference transform.py:114-156: 8 augmented evaluations per patch, averaged
+  int variants() const { return (p.augment && p.framework == CFB_FRAMEWORK_UNET3L) ? 8 : 1; }
+
   ~cfb_engine() {
     cudaSetDevice(p.device);
     net.release();
@@ -179,8 +182,9 @@ void prepare_chunk(cfb_engine* e, int64_t cz, int64_t cy, int64_t cx, cudaStream
   for (size_t a = 0; a < e->gz.in_start.size(); ++a)
     for (size_t b = 0; b < e->gy.in_start.size(); ++b)
       for (size_t c = 0; c < e->gx.in_start.size(); ++c)
-        e->h_patches.push_back(PatchPos{e->gz.in_start[a], e->gy.in_start[b], e->gx.in_start[c],
-                                        e->gz.out_start[a], e->gy.out_start[b], e->gx.out_start[c]});
+        for (int v = 0; v < e->variants(); ++v)  // 8 flip/transpose variants per patch with --augment
+          e->h_patches.push_back(PatchPos{e->gz.in_start[a], e->gy.in_start[b], e->gx.in_start[c],
+                                          e->gz.out_start[a], e->gy.out_start[b], e->gx.out_start[c], v});
   if (e->h_patches.empty()) throw std::invalid_argument("no patch fits the chunk");
   cudaFree(e->d_patches); e->d_patches = nullptr;
   CFB_CUDA(cudaMalloc(&e->d_patches, e->h_patches.size() * sizeof(PatchPos)));
@@ -253,7 +257,8 @@ void run_patches(cfb_engine* e, const void* d_in, int in_dtype, int64_t first, i
   const Int3 cs = e->cached_chunk;
   const int C = e->p.num_output_channels;
   const int B = std::max(1, e->p.batch_size);
-  const int64_t per_row = (int64_t)e->gy.in_start.size() * e->gx.in_start.size();
+  const int64_t per_row = (int64_t)e->gy.in_start.size() * e->gx.in_start.size() * e->variants();
+  const float scale = 1.0f / (float)e->variants();
   for (int64_t i = first; i < last; i += B) {
     const int nb = (int)std::min<int64_t>(B, last - i);
     if (pg) {
@@ -266,7 +271,7 @@ void run_patches(cfb_engine* e, const void* d_in, int in_dtype, int64_t first, i
       launch_identity_blend(d_in, in_dtype, cs, e->ip, e->op, e->pcrop, e->d_mask, pp, nb, d_out, C, e->out_size, s);
       e->launches++;
     } else {
-      e->launches += e->net.forward_and_blend(d_in, in_dtype, cs, pp, nb, e->op, e->pcrop, e->d_mask, d_out, C, e->out_size, s);
+      e->launches += e->net.forward_and_blend(d_in, in_dtype, cs, pp, nb, e->op, e->pcrop, e->d_mask, d_out, C, e->out_size, scale, s);
     }
   }
 }
@@ -300,7 +305,7 @@ int infer_impl(cfb_engine* e, const void* d_in, int in_dtype, int64_t cz, int64_
     else if (e->p.mask_output_chunk) { ensure_winv(e, s); pg->winv = e->d_winv; }
   }
   CFB_CUDA(cudaEventRecord(e->ev[1], s));
-  run_patches(e, d_in, in_dtype, zrow_begin * ny * nx, zrow_end * ny * nx, d_out, s, pg);
+  run_patches(e, d_in, in_dtype, zrow_begin * ny * nx * e->variants(), zrow_end * ny * nx * e->variants(), d_out, s, pg);
   CFB_CUDA(cudaEventRecord(e->ev[2], s));
   if (slab) {
     // partial weight sum of this slab's patches only
@@ -376,7 +381,8 @@ int cfb_create(const cfb_params* params, cfb_handle* out) {
     if (p.framework != CFB_FRAMEWORK_UNET3L && p.framework != CFB_FRAMEWORK_IDENTITY) throw std::invalid_argument("unknown framework");
     if (p.num_input_channels != 1) throw std::invalid_argument("only one input channel is supported");
     if (p.num_output_channels < 1 || p.num_output_channels > 8) throw std::invalid_argument("num_output_channels must be in [1, 8]");
-    if (p.augment) { set_last_error("test-time augmentation is not implemented on the device yet"); return CFB_ERR_UNSUPPORTED; }
+    if (p.augment && p.framework == CFB_FRAMEWORK_UNET3L && p.input_patch_size[1] != p.input_patch_size[2])
+      throw std::invalid_argument("test-time augmentation transposes y and x: the patch must be square in y, x");
     auto e = std::make_unique<cfb_engine>();
     e->p = p;
     e->ip = Int3{p.input_patch_size[0], p.input_patch_size[1], p.input_patch_size[2]};

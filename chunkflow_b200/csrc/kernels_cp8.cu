@@ -92,17 +92,19 @@ first_conv_cp8_kernel(const void* __restrict__ src, Int3 cs, const PatchPos* __r
   const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
   const int z = blockIdx.y, b = blockIdx.z;
   const int x0 = tile_x * kFX, y0 = tile_y * kFY;
-  int oz = 0, oy = 0, ox = 0;
-  if (SRC != 2) { const PatchPos pp = patches[b]; oz = pp.iz; oy = pp.iy; ox = pp.ix; }
+  int oz = 0, oy = 0, ox = 0, flags = 0;
+  if (SRC != 2) { const PatchPos pp = patches[b]; oz = pp.iz; oy = pp.iy; ox = pp.ix; flags = pp.flags; }
   for (int i = threadIdx.x; i < 3 * (kFY + 2) * (kFX + 2); i += kT) {
     const int c = i % (kFX + 2), r = (i / (kFX + 2)) % (kFY + 2), d = i / ((kFX + 2) * (kFY + 2));
     const int gz = z + d - 1, gy = y0 + r - 1, gx = x0 + c - 1;
     float v = 0.f;  // zero padding at the PATCH border
     if (gz >= 0 && gz < ps.z && gy >= 0 && gy < ps.y && gx >= 0 && gx < ps.x) {
+      int sy = gy, sx = gx;
+      if (SRC != 2 && flags) tta_map(flags, ps.y, ps.x, gy, gx, sy, sx);  // augmented variant reads the original patch
       if (SRC == 0) {
-        v = __fdiv_rn((float)static_cast<const uint8_t*>(src)[((size_t)(oz + gz) * cs.y + (oy + gy)) * cs.x + ox + gx], 255.0f);
+        v = __fdiv_rn((float)static_cast<const uint8_t*>(src)[((size_t)(oz + gz) * cs.y + (oy + sy)) * cs.x + ox + sx], 255.0f);
       } else if (SRC == 1) {
-        v = static_cast<const float*>(src)[((size_t)(oz + gz) * cs.y + (oy + gy)) * cs.x + ox + gx];
+        v = static_cast<const float*>(src)[((size_t)(oz + gz) * cs.y + (oy + sy)) * cs.x + ox + sx];
       } else {
         v = static_cast<const float*>(src)[(((size_t)b * ps.z + gz) * ps.y + gy) * ps.x + gx];
       }
@@ -240,7 +242,8 @@ head_sigmoid_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ 
 __global__ void __launch_bounds__(kT)
 head_blend_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias, int cin,
                       int cnet, int parts, Int3 ip, Int3 op, Int3 crop, const float* __restrict__ mask,
-                      const PatchPos* __restrict__ patches, int nb, float* __restrict__ out, int channels, Int3 os) {
+                      const PatchPos* __restrict__ patches, int nb, float* __restrict__ out, int channels, Int3 os,
+                      float scale) {
   extern __shared__ float s_hw[];  // [channels][cin] + [channels]
   for (int i = threadIdx.x; i < channels * cin; i += blockDim.x) s_hw[i] = w[i];
   for (int i = threadIdx.x; i < channels; i += blockDim.x) s_hw[channels * cin + i] = bias[i];
@@ -254,7 +257,9 @@ head_blend_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
     const int b = (int)(i / opvol);
     const int x = (int)(ov % op.x), y = (int)((ov / op.x) % op.y), z = (int)(ov / ((size_t)op.x * op.y));
     const PatchPos pp = patches[b];
-    const int gz = pp.oz + z, gy = pp.oy + y, gx = pp.ox + x;
+    int sy = y, sx = x;
+    if (pp.flags) tta_map(pp.flags, op.y, op.x, y, x, sy, sx);  // write an augmented variant back un-transformed
+    const int gz = pp.oz + z, gy = pp.oy + sy, gx = pp.ox + sx;
     if (gz < 0 || gz >= os.z || gy < 0 || gy >= os.y || gx < 0 || gx >= os.x) continue;  // clipped
     const size_t iv = ((size_t)(z + crop.z) * ip.y + (y + crop.y)) * ip.x + (x + crop.x);
     float acc[8];
@@ -266,7 +271,7 @@ head_blend_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
       for (int e = 0; e < 8; ++e)
         for (int co = 0; co < channels; ++co) acc[co] = fmaf(v[e], s_hw[co * cin + ch * 8 + e], acc[co]);
     }
-    const float m = __ldg(mask + ov);
+    const float m = __ldg(mask + ov) * scale;
     float* dst = out + ((size_t)gz * os.y + gy) * os.x + gx;
     for (int co = 0; co < channels; ++co) {
       const float sig = __fdiv_rn(1.0f, 1.0f + expf(-acc[co]));
@@ -341,12 +346,12 @@ void launch_convT_cp8(const __half* in, const float* w, const float* bias, __hal
 
 void launch_head_blend_cp8(const __half* in, const float* w, const float* bias, int cin, int cnet, int parts, Int3 ip,
                            Int3 op, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out, int channels,
-                           Int3 os, cudaStream_t s) {
+                           Int3 os, float scale, cudaStream_t s) {
   if (channels > 8 || channels > cnet) throw std::runtime_error("head_blend: bad channel count");
   const size_t smem = (size_t)(channels * cin + channels) * sizeof(float);
   // only the first `channels` rows of the head are evaluated (reference patch/base.py:70-74 keeps the first N)
   head_blend_cp8_kernel<<<grid_for((size_t)nb * vol(op)), kT, smem, s>>>(reinterpret_cast<const uint4*>(in), w, bias, cin, cnet,
-                                                                        parts, ip, op, crop, mask, patches, nb, out, channels, os);
+                                                                        parts, ip, op, crop, mask, patches, nb, out, channels, os, scale);
   CFB_LAUNCH_CHECK();
 }
 

@@ -42,7 +42,16 @@ extract_patches_kernel(const T* __restrict__ chunk, Int3 cs, const PatchPos* __r
     const PatchPos pp = patches[b];
     const T* src = chunk + ((int64_t)(pp.iz + z) * cs.y + (pp.iy + y)) * cs.x + pp.ix + xq * 4;
     float4 v;
-    if constexpr (sizeof(T) == 1) {
+    if (pp.flags) {  // test-time augmentation variant: gather through the coordinate map
+      float e[4];
+      for (int k = 0; k < 4; ++k) {
+        int sy, sx;
+        tta_map(pp.flags, p.y, p.x, y, xq * 4 + k, sy, sx);
+        const T raw = chunk[((int64_t)(pp.iz + z) * cs.y + (pp.iy + sy)) * cs.x + pp.ix + sx];
+        if constexpr (sizeof(T) == 1) e[k] = u8_to_unit(raw); else e[k] = raw;
+      }
+      v = make_float4(e[0], e[1], e[2], e[3]);
+    } else if constexpr (sizeof(T) == 1) {
       if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
         unsigned int w = __ldg(reinterpret_cast<const unsigned int*>(src));
         v = make_float4(u8_to_unit(w & 0xff), u8_to_unit((w >> 8) & 0xff), u8_to_unit((w >> 16) & 0xff),
@@ -78,9 +87,24 @@ blend_patches_kernel(const float* __restrict__ net, int cnet, Int3 ip, Int3 op, 
     int b = (int)(r / op.z);
     const PatchPos pp = patches[b];
     const int x = xq * 4;
+    const int nx = min(4, op.x - x);
+    if (pp.flags) {  // augmented variant: scatter back through the coordinate map, element by element
+      const int gz = pp.oz + z;
+      if (gz < 0 || gz >= os.z) continue;
+      for (int k = 0; k < nx; ++k) {
+        int sy, sx;
+        tta_map(pp.flags, op.y, op.x, y, x + k, sy, sx);
+        const int gy = pp.oy + sy, gx = pp.ox + sx;
+        if (gy < 0 || gy >= os.y || gx < 0 || gx >= os.x) continue;
+        const float mk = mask ? __ldg(mask + ((int64_t)z * op.y + y) * op.x + x + k) : 1.f;
+        const float* sp = net + (int64_t)b * cnet * in_vol + ((int64_t)(z + crop.z) * ip.y + (y + crop.y)) * ip.x + (x + k + crop.x);
+        float* dp = out + ((int64_t)gz * os.y + gy) * os.x + gx;
+        for (int c = 0; c < channels; ++c) red_add_f32(dp + (int64_t)c * out_vol, sp[(int64_t)c * in_vol] * scale * mk);
+      }
+      continue;
+    }
     const int gz = pp.oz + z, gy = pp.oy + y, gx = pp.ox + x;
     if (gz < 0 || gz >= os.z || gy < 0 || gy >= os.y) continue;  // clipped (chunk/base.py:793-796)
-    const int nx = min(4, op.x - x);
     const float* m = mask ? mask + ((int64_t)z * op.y + y) * op.x + x : nullptr;
     const float* src = net + (int64_t)b * cnet * in_vol +
                        ((int64_t)(z + crop.z) * ip.y + (y + crop.y)) * ip.x + (x + crop.x);

@@ -163,6 +163,7 @@ struct FusedTail {
   float* out;            // (channels, os.z, os.y, os.x)
   int channels;
   Int3 op, crop, os;
+  float scale;
 };
 
 template <int COUT, bool SPLIT>
@@ -192,9 +193,11 @@ __device__ __forceinline__ void head_blend_16(const float (&v)[16], const FusedT
                                               const PatchPos& pp, int z, int y, int x) {
   const int oz = z - t.crop.z, oy = y - t.crop.y, ox = x - t.crop.x;  // coordinates in the cropped output patch
   if (oz < 0 || oz >= t.op.z || oy < 0 || oy >= t.op.y || ox < 0 || ox >= t.op.x) return;
-  const int gz = pp.oz + oz, gy = pp.oy + oy, gx = pp.ox + ox;
+  int sy = oy, sx = ox;
+  if (pp.flags) tta_map(pp.flags, t.op.y, t.op.x, oy, ox, sy, sx);  // augmented variant: write back un-transformed
+  const int gz = pp.oz + oz, gy = pp.oy + sy, gx = pp.ox + sx;
   if (gz < 0 || gz >= t.os.z || gy < 0 || gy >= t.os.y || gx < 0 || gx >= t.os.x) return;  // clipped by the chunk
-  const float m = __ldg(t.mask + ((size_t)oz * t.op.y + oy) * t.op.x + ox);
+  const float m = __ldg(t.mask + ((size_t)oz * t.op.y + oy) * t.op.x + ox) * t.scale;
   float* dst = t.out + ((size_t)gz * t.os.y + gy) * t.os.x + gx;
   const size_t out_vol = (size_t)t.os.z * t.os.y * t.os.x;
   for (int co = 0; co < t.channels; ++co) {
@@ -1195,6 +1198,7 @@ void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, c
     if (tail->channels > 8) throw std::runtime_error("fused tail: at most 8 channels");
     ft.head_w = tail->head_w; ft.head_b = tail->head_b; ft.patches = tail->patches; ft.mask = tail->mask; ft.out = tail->out;
     ft.channels = tail->channels; ft.op = tail->out_patch; ft.crop = tail->crop; ft.os = tail->out_size;
+    ft.scale = tail->scale;
   }
   if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
   else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);

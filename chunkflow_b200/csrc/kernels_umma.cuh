@@ -55,6 +55,7 @@ struct ConvTail {
   float* out;               // device, (channels, out_size)
   int channels;
   Int3 out_patch, crop, out_size;
+  float scale;              // 1, or 1/8 when the batch holds the 8 test-time-augmentation variants
 };
 void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out,
                        int nb, Int3 size, bool relu, cudaStream_t s, const ConvTail* tail = nullptr);
@@ -85,7 +86,7 @@ void launch_convT_cp8(const __half* in, const float* w, const float* bias, __hal
 // red.global.add -- the raw network output never touches HBM.
 void launch_head_blend_cp8(const __half* in, const float* w, const float* bias, int cin, int cnet, int parts, Int3 in_patch,
                            Int3 out_patch, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out,
-                           int channels, Int3 out_size, cudaStream_t s);
+                           int channels, Int3 out_size, float scale, cudaStream_t s);
 
 // 1x1x1 head + sigmoid -> planar fp32 (nb, cout, Z,Y,X).
 void launch_head_sigmoid_cp8(const __half* in, const float* w, const float* bias, float* out, int cin, int cout,

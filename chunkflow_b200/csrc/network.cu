@@ -247,15 +247,15 @@ int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const 
 }
 
 int Network::forward_and_blend(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, Int3 op, Int3 crop,
-                               const float* mask, float* out, int channels, Int3 out_size, cudaStream_t s) {
+                               const float* mask, float* out, int channels, Int3 out_size, float scale, cudaStream_t s) {
   if (nb > batch_) throw std::invalid_argument("batch larger than configured");
   if (umma() && !getenv("CFB_NO_FUSED_TAIL")) {
     const ConvLayer& H = layers_.at("head");
-    ConvTail tail{H.w, H.bias, patches, mask, out, channels, op, crop, out_size};
+    ConvTail tail{H.w, H.bias, patches, mask, out, channels, op, crop, out_size, scale};
     return forward_cp8(chunk, in_dtype, cs, patches, nb, s, /*with_head=*/false, &tail);
   }
   int n = forward_from_chunk(chunk, in_dtype, cs, patches, nb, s);
-  return n + blend(op, crop, mask, patches, nb, out, channels, out_size, s);
+  return n + blend(op, crop, mask, patches, nb, out, channels, out_size, scale, s);
 }
 
 int Network::forward_from_host_patches(const float* h_patches, int nb, cudaStream_t s) {
@@ -266,16 +266,16 @@ int Network::forward_from_host_patches(const float* h_patches, int nb, cudaStrea
 }
 
 int Network::blend(Int3 op, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out, int channels,
-                   Int3 out_size, cudaStream_t s) {
+                   Int3 out_size, float scale, cudaStream_t s) {
   if (umma()) {
     const ConvLayer& L = layers_.at("head");
     prof_begin("head+blend", s);
-    launch_head_blend_cp8(h_d0_, L.w, L.bias, 16, cnet_, parts(), patch_, op, crop, mask, patches, nb, out, channels, out_size, s);
+    launch_head_blend_cp8(h_d0_, L.w, L.bias, 16, cnet_, parts(), patch_, op, crop, mask, patches, nb, out, channels, out_size, scale, s);
     prof_end(s);
     return 1;
   }
   prof_begin("blend", s);
-  launch_blend_patches(net_out_, cnet_, patch_, op, crop, mask, patches, nb, out, channels, out_size, 1.0f, s);
+  launch_blend_patches(net_out_, cnet_, patch_, op, crop, mask, patches, nb, out, channels, out_size, scale, s);
   prof_end(s);
   return 1;
 }

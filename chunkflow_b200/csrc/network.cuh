@@ -34,10 +34,10 @@ class Network {
   // Whole-chunk path: extract + network + crop + bump mask + accumulate into the output chunk.  On the tcgen05
   // path the head and the blend are fused into the epilogue of the last convolution.
   int forward_and_blend(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, Int3 out_patch,
-                        Int3 crop, const float* mask, float* out, int channels, Int3 out_size, cudaStream_t s);
+                        Int3 crop, const float* mask, float* out, int channels, Int3 out_size, float scale, cudaStream_t s);
   // crop + bump mask + accumulate the last forward's outputs into the output chunk.
   int blend(Int3 out_patch, Int3 crop, const float* mask, const PatchPos* patches, int nb, float* out,
-            int channels, Int3 out_size, cudaStream_t s);
+            int channels, Int3 out_size, float scale, cudaStream_t s);
   void crop_mask(Int3 out_patch, Int3 crop, const float* mask, int nb, float* dst, int channels, cudaStream_t s);
   float* patch_input_buffer(int nb);
   void copy_raw_output_to_host(float* h_out, cudaStream_t s);

@@ -130,7 +130,7 @@ class Inferencer(object):
         self._prepare_patch_inferencer(framework, convnet_model, convnet_weight_path, bump, precision)
 
     # ------------------------------------------------------------------------------------
-    def _engine(self, framework_code, precision=None, plugin=False):
+    def _engine(self, framework_code, precision=None, augment=False):
         return _native.Engine(
             input_patch_size=self.input_patch_size,
             # a host plugin returns cropped patches: to the device they are crop-free patches
@@ -145,6 +145,7 @@ class Inferencer(object):
             precision=b200_patch.precision_code(self.dtype, precision),
             device=self.device,
             mask_myelin_threshold=self.mask_myelin_threshold,
+            augment=augment,
             check_output_range=True)
 
     def _prepare_patch_inferencer(self, framework, convnet_model, convnet_weight_path, bump, precision):
@@ -155,9 +156,9 @@ class Inferencer(object):
                 "(chunkflow_b200/convnet/unet3l.py) only; arbitrary torch models have no CPU/eager fallback here. "
                 "Wrap other backends as a `universal` plugin.")
         if framework in ('b200', 'pytorch'):
-            if self.transform_sequences is not None:
-                raise NotImplementedError('--augment is not available on the device network path yet')
-            self.engine = self._engine(_native.FRAMEWORK_UNET3L, precision)
+            # --augment: the 8 flip/transpose variants of every patch run as 8 batch entries on the device and
+            # are averaged by the blend (spatial flips, see transform.py for the deviation from the reference)
+            self.engine = self._engine(_native.FRAMEWORK_UNET3L, precision, augment=self.transform_sequences is not None)
             self.engine.load_state_dict(b200_patch.load_state_dict(convnet_model, convnet_weight_path))
         elif framework == 'identity':
             if self.transform_sequences is not None:

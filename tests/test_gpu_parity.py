@@ -325,3 +325,21 @@ def test_slab_entry_point_matches_whole_chunk():
     eng.normalize_device(d_acc.data_ptr(), d_w.data_ptr(), d_acc.shape)
     torch.cuda.synchronize()
     np.testing.assert_allclose(d_acc.cpu().numpy(), whole, rtol=0, atol=BLEND_ATOL)
+
+
+@pytest.mark.parametrize("precision", ["f16x3", "simt"])
+def test_device_test_time_augmentation(unet_model, precision):
+    """--augment on the device network path: 8 spatial flip/transpose variants per patch, averaged.
+    Checked against the oracle's `spatial` augmentation (the product's documented deviation from the
+    reference's channel/batch-axis flips)."""
+    rng = np.random.default_rng(29)
+    img = rng.integers(0, 256, size=(10, 40, 44), dtype=np.uint8)
+    kw = dict(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3)
+    inf = _inferencer(model=MODEL_FILE, framework="b200", batch_size=8, augment=True, precision=precision, **kw)
+    out = inf(Chunk(img))
+    o, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, augment="spatial", **kw)
+    plain, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, **kw)
+    err = np.abs(out.array - o).max()
+    print("device TTA max-abs", precision, err, "| TTA changes the result by", np.abs(o - plain).max())
+    assert err <= (NET_ATOL_F32 if precision == "f16x3" else NET_ATOL_SIMT)
+    assert np.abs(o - plain).max() > 1e-2   # the augmentation is not a no-op for a real network

@@ -226,6 +226,7 @@ struct UmmaConvParams {
   int T;          // z-stacked kernel: output planes per job
   const __half* wpacked_zs;  // z-stacked weight blocks
   FusedTail tail;  // used by the TAIL = true instantiations only
+  int total_items; // z-stacked kernel: work items = batch x tiles x z blocks (persistent CTAs)
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
@@ -492,10 +493,15 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tx = blockIdx.x % p.tiles_x;
-  const int ty = (blockIdx.x / p.tiles_x) % p.tiles_y;
-  const int b = blockIdx.x / (p.tiles_x * p.tiles_y);
-  const int x0 = tx * p.XT, y0 = ty * p.TY;
+  // Persistent CTA: work item = (batch, y tile, x tile, z block); item i is handled by CTA i mod gridDim.x, every
+  // warp role walks the same item sequence.  Items are independent (each loads its own halo planes).
+  const int njobs = (p.Z + p.T - 1) / p.T;
+  const int ncols = p.tiles_x * p.tiles_y;
+  struct Item { int b, x0, y0, z0; };
+  auto item_of = [&](int item) {
+    const int j = item % njobs, col = item / njobs;
+    return Item{col / ncols, (col % p.tiles_x) * p.XT, ((col / p.tiles_x) % p.tiles_y) * p.TY, j * p.T};
+  };
 
   uint8_t* sA = smem;
   uint8_t* sB = smem + kRing * p.slot_stride;
@@ -509,7 +515,6 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   if constexpr (TAIL) {
     for (int i = threadIdx.x; i < p.tail.channels * 16; i += kThreads) s_head[i] = p.tail.head_w[i];
     for (int i = threadIdx.x; i < p.tail.channels; i += kThreads) s_head[p.tail.channels * 16 + i] = p.tail.head_b[i];
-    pp = p.tail.patches[b];
   }
 
   if (threadIdx.x == 0) {
@@ -529,17 +534,18 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   const int Z = p.Z, T = p.T;
-  const int njobs = (Z + T - 1) / T;
 
   if (warp == 0) {
     // ---------------- A producer: for every job its input planes max(z0-1,0) .. min(z0+T, Z-1) ----------------
     if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
-      const int plane_a0 = b * p.planes_a * P, plane_b0 = b * p.planes_b * P;
       int slot = 0, ld = 0;
       uint32_t prev_parity = 1;
-      for (int j = 0; j < njobs; ++j) {
-        const int z0 = j * T, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const Item it = item_of(item);
+        const int x0 = it.x0, y0 = it.y0, z0 = it.z0;
+        const int plane_a0 = it.b * p.planes_a * P, plane_b0 = it.b * p.planes_b * P;
+        const int qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
         for (int q = qlo; q <= qhi; ++q, ++ld) {
           if (ld >= kRing) mbar_wait(BAR(3 + slot), prev_parity);
           mbar_expect_tx(BAR(slot), tx_bytes);
@@ -562,7 +568,10 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t per_plane = 9u * Cfg::KG;
       const uint32_t nbs = (uint32_t)p.bstages;
       uint32_t planes = 0;
-      for (int j = 0; j < njobs; ++j) planes += (uint32_t)(min(j * T + T, Z - 1) - max(j * T - 1, 0) + 1);
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int z0 = item_of(item).z0;
+        planes += (uint32_t)(min(z0 + T, Z - 1) - max(z0 - 1, 0) + 1);
+      }
       const uint32_t total = p.bresident ? per_plane : planes * per_plane;
       uint32_t st = 0, blk = 0, prev_parity = 1;
       for (uint32_t i = 0; i < total; ++i) {
@@ -591,11 +600,12 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       uint32_t ring_st = 0, ring_parity = 0;
       uint32_t slot = 0, sparity = 0;
       bool first_plane = true;
-      for (int j = 0; j < njobs; ++j) {
-        const uint32_t buf = (uint32_t)j & 1u;
-        mbar_wait(BAR(kAccE + buf), (uint32_t)(j >> 1) & 1u);  // zeroed by the epilogue (initially and after draining)
+      int jj = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
+        const uint32_t buf = (uint32_t)jj & 1u;
+        mbar_wait(BAR(kAccE + buf), (uint32_t)(jj >> 1) & 1u);  // zeroed by the epilogue (initially and after draining)
         tc_fence_after();
-        const int z0 = j * T, z1 = min(z0 + T, Z), qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+        const int z0 = item_of(item).z0, z1 = min(z0 + T, Z), qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
         const uint32_t dbuf = tmem_base + buf * kBufCols;
         for (int q = qlo; q <= qhi; ++q) {
           mbar_wait(BAR(slot), sparity);
@@ -658,14 +668,17 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       mbar_arrive(BAR(kAccE + 0));
       mbar_arrive(BAR(kAccE + 1));
     }
-    const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
     const size_t plane_vox = (size_t)p.Z * p.Y * p.X;
     const float inv_pitch = 1.0f / (float)p.pitch;
     uint4* out16 = reinterpret_cast<uint4*>(p.out);
-    for (int j = 0; j < njobs; ++j) {
-      const int buf = j & 1;
-      const int z0 = j * T, z1 = min(z0 + T, Z);
-      mbar_wait(BAR(kAccF + buf), (uint32_t)(j >> 1) & 1u);
+    int jj = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
+      const int buf = jj & 1;
+      const Item it = item_of(item);
+      const int b = it.b, x0 = it.x0, y0 = it.y0, z0 = it.z0, z1 = min(z0 + T, Z);
+      const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
+      if constexpr (TAIL) pp = p.tail.patches[b];
+      mbar_wait(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u);
       tc_fence_after();
       for (int g = 0; g < p.G; ++g) {
         const int m = wq * 32 + lane;
@@ -1002,7 +1015,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
     }
     // z-stacked variants: T output planes per job, accumulators (G * T * NB columns) per TMEM buffer
     if (3 * Cfg::NB <= 256 && !getenv("CFB_NO_ZSTACK")) {
-      for (int T : {2, 4, 8}) {
+      for (int T : {2, 3, 4, 6, 8}) {
         if (T > sz.z && T != 2) continue;
         for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
           const size_t plane = (size_t)(tyc + 2) * pitch * 16;
@@ -1021,9 +1034,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
           t.T = T; t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
           const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
           const double lookahead = t.resident ? 1e9 : (double)(bs - 1) * G * Cfg::KS * Cfg::P * 3;
-          const int ctas = nb * ceil_div(sz.x, XT) * ceil_div(sz.y, tyc);
-          const double waves = (double)ctas / sm_count;
-          const double quant = std::ceil(waves) / waves;
+          const double quant = 1.0;  // persistent CTAs over (column, z block) items: no wave quantisation
           // one tile read serves three z-taps: (T + 2) / (3 T) of the plain kernel's operand traffic
           t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T) + 0.25)) * quant +
                    (lookahead >= 96 ? 0.0 : 0.4 * (96 - lookahead) / 96);
@@ -1041,6 +1052,8 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
   std::sort(out.begin(), out.end(), [](const ConvTile& a, const ConvTile& b) { return a.cost < b.cost; });
   return out;
 }
+
+int sm_count();
 
 template <int CIN, int COUT, bool SPLIT>
 void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w,
@@ -1068,7 +1081,11 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + kBarBytes + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
-  const int grid = nb * p.tiles_x * p.tiles_y;
+  int grid = nb * p.tiles_x * p.tiles_y;
+  if (t.T) {  // persistent CTAs striding over (column, z block) work items
+    p.total_items = grid * ceil_div(sz.z, t.T);
+    grid = std::min<int>(p.total_items, sm_count());
+  }
   auto run = [&](auto kern) {
     CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, s>>>(mapA, mapB, p);
@@ -1123,7 +1140,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       CFB_CUDA(cudaEventCreate(&e0));
       CFB_CUDA(cudaEventCreate(&e1));
       float best_ms = 1e30f;
-      const size_t n = std::min<size_t>(cands.size(), 24);
+      const size_t n = std::min<size_t>(cands.size(), 32);
       for (size_t i = 0; i < n; ++i) {
         launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
         CFB_CUDA(cudaEventRecord(e0, s));

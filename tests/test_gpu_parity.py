@@ -155,7 +155,7 @@ def test_conv3_layer_tcgen05_split_against_torch(cin, cout, size):
     _conv3_case(_native.PRECISION_F16X3_UMMA, cin, cout, size, 5e-5)
 
 
-@pytest.mark.parametrize("zstack", ["2", "4", "8"])
+@pytest.mark.parametrize("zstack", ["2", "3", "4", "8"])
 @pytest.mark.parametrize("cin,cout,size", [(16, 16, (3, 8, 40)), (16, 16, (9, 16, 70)), (32, 32, (5, 12, 20)), (16, 32, (4, 6, 128)),
                                            (32, 16, (7, 8, 130)), (64, 32, (4, 16, 16)), (16, 16, (1, 7, 9))])
 def test_conv3_layer_tcgen05_zstacked_kernel(monkeypatch, zstack, cin, cout, size):

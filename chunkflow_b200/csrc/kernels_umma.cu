@@ -920,6 +920,171 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
 }
 
 // ------------------------------------------------------------------------------------------
+// First layer (Cin = 1) on tcgen05, fused with patch extraction: the 27 taps of a voxel are the K
+// dimension (padded to 32).  Producer warps gather the uint8 neighbourhood of 128 consecutive x
+// positions straight from the chunk (through the test-time-augmentation coordinate map) and write
+// the im2col tile in the canonical K-major layout; uint8 values are exact in fp16, so one MMA
+// pass x [w_hi | w_lo] gives the fp32-accurate sum of w * x, and the epilogue divides by 255
+// (the reference normalises x / 255 first: inferencer.py:395-399), adds bias, ReLU, writes CP8.
+// ------------------------------------------------------------------------------------------
+struct FirstConvParams {
+  const uint8_t* chunk;
+  Int3 cs;
+  const PatchPos* patches;
+  Int3 ps;
+  const __half* wpacked;  // [4 chunks of 8 taps][NBR rows][8]
+  const float* bias;
+  __half* out;
+  int tiles_x, total_tiles;
+};
+
+constexpr int kFcThreads = 288;  // 4 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kFcAcc = 4;        // accumulator slots in TMEM
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kFcThreads, 1) first_conv_umma_kernel(const FirstConvParams p) {
+  constexpr int P = SPLIT ? 2 : 1;
+  constexpr int NBR = 16 * P;           // weight rows: hi (16) | lo (16)
+  constexpr int ABYTES = 4 * 128 * 16;  // one im2col tile: 4 K-chunks x 128 rows x 16 B
+  constexpr int WBYTES = 4 * NBR * 16;
+  __shared__ __align__(128) uint8_t sA[2][ABYTES];
+  __shared__ __align__(128) uint8_t sW[WBYTES];
+  __shared__ __align__(8) uint64_t bars[2 + 2 + 2 * kFcAcc + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // [0,1] a_full (128 producer arrivals)  [2,3] a_empty  [4..7] acc_full  [8..11] acc_empty (128)  [12] w_full
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(i), 128); mbar_init(BAR(2 + i), 1); }
+    for (int i = 0; i < kFcAcc; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(8 + i), 128); }
+    mbar_init(BAR(12), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int X = p.ps.x, Y = p.ps.y, Z = p.ps.z;
+
+  auto tile_of = [&](int t, int& b, int& z, int& y, int& x0) {
+    x0 = (t % p.tiles_x) * 128;
+    int r = t / p.tiles_x;
+    y = r % Y; r /= Y;
+    z = r % Z;
+    b = r / Z;
+  };
+
+  if (warp < 4) {
+    // ---------------- producers: im2col tile of 128 x-positions ----------------
+    const int m = threadIdx.x;
+    int k = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++k) {
+      const int buf = k & 1;
+      if (k >= 2) mbar_wait(BAR(2 + buf), ((k >> 1) - 1) & 1);
+      int b, z, y, x0;
+      tile_of(t, b, z, y, x0);
+      const PatchPos pp = p.patches[b];
+      const int x = x0 + m;
+      uint32_t h[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) h[i] = 0u;
+      if (x < X) {
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+          const int zz = z + tap / 9 - 1, yy = y + (tap / 3) % 3 - 1, xx = x + tap % 3 - 1;
+          float v = 0.f;
+          if (zz >= 0 && zz < Z && yy >= 0 && yy < Y && xx >= 0 && xx < X) {
+            int sy = yy, sx = xx;
+            if (pp.flags) tta_map(pp.flags, Y, X, yy, xx, sy, sx);
+            v = (float)__ldg(p.chunk + ((size_t)(pp.iz + zz) * p.cs.y + (pp.iy + sy)) * p.cs.x + pp.ix + sx);
+          }
+          const uint32_t hv = (uint32_t)__half_as_ushort(__float2half_rn(v));
+          h[tap >> 1] |= (tap & 1) ? (hv << 16) : hv;
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(sA[buf]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dst[c * 128 + m] = make_uint4(h[c * 4], h[c * 4 + 1], h[c * 4 + 2], h[c * 4 + 3]);
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      mbar_arrive(BAR(buf));
+    }
+  } else if (warp == 4) {
+    // ---------------- MMA issuer ----------------
+    if (elect_one()) {
+      mbar_expect_tx(BAR(12), WBYTES);
+      bulk_load(smem_u32(sW), p.wpacked, WBYTES, BAR(12));
+      mbar_wait(BAR(12), 0);
+      tc_fence_after();
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
+      constexpr uint32_t IDESC = make_idesc(NBR);
+      auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+      const uint32_t w16 = smem_u32(sW) >> 4;
+      int k = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++k) {
+        const int buf = k & 1, a = k % kFcAcc;
+        if (k >= kFcAcc) mbar_wait(BAR(8 + a), ((k / kFcAcc) - 1) & 1);
+        mbar_wait(BAR(buf), (k >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a16 = smem_u32(sA[buf]) >> 4;
+        const uint32_t d = tmem_base + (uint32_t)a * NBR;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)  // K = 32 taps = two K=16 steps = chunk pairs (0,1), (2,3)
+          tc_mma_f16(d, desc((128u << 16) | (a16 + ks * 256)), desc(((uint32_t)NBR << 16) | (w16 + ks * 2 * NBR)), IDESC,
+                     ks ? 1u : 0u);
+        tc_commit(BAR(2 + buf));
+        tc_commit(BAR(4 + a));
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    const int wq = warp & 3;
+    const size_t plane_vox = (size_t)Z * Y * X;
+    uint4* out16 = reinterpret_cast<uint4*>(p.out);
+    int k = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++k) {
+      const int a = k % kFcAcc;
+      int b, z, y, x0;
+      tile_of(t, b, z, y, x0);
+      mbar_wait(BAR(4 + a), (k / kFcAcc) & 1);
+      tc_fence_after();
+      const int x = x0 + wq * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)a * NBR;
+      uint32_t r[16];
+      tc_ld16(taddr, r);
+      float v[16];
+      if (SPLIT) {
+        uint32_t r2[16];
+        tc_ld16(taddr + 16, r2);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+      } else {
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(8 + a));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(__fdiv_rn(v[i], 255.0f) + __ldg(p.bias + i), 0.f);
+      if (x < X) store_cp8_16<16, SPLIT>(v, 0, b, ((size_t)z * Y + y) * X + x, plane_vox, out16);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Host side: tensor maps, tile selection, launch
 // ------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
@@ -1300,6 +1465,41 @@ void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout
   CFB_CUDA(cudaMemcpy(out.w, buf.data(), out.bytes, cudaMemcpyHostToDevice));
   CFB_CUDA(cudaMalloc(&out.bias, cout * sizeof(float)));
   CFB_CUDA(cudaMemcpy(out.bias, h_bias, cout * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void pack_first_conv_weights(const float* h_w, const float* h_bias, int parts, PackedConv& out) {
+  free_packed(out);
+  const int NBR = 16 * parts;
+  std::vector<__half> buf((size_t)4 * NBR * 8, __float2half_rn(0.f));
+  for (int c = 0; c < 4; ++c)
+    for (int n = 0; n < NBR; ++n)
+      for (int e = 0; e < 8; ++e) {
+        const int tap = c * 8 + e;
+        if (tap >= 27) continue;
+        const float wv = h_w[(size_t)(n % 16) * 27 + tap];  // (16, 1, 3, 3, 3)
+        const __half hi = __float2half_rn(wv);
+        buf[((size_t)c * NBR + n) * 8 + e] = n < 16 ? hi : __float2half_rn(wv - __half2float(hi));
+      }
+  out.cin = 1; out.cout = 16; out.parts = parts;
+  out.tuned = std::make_shared<std::map<uint64_t, ConvTile>>();
+  out.bytes = buf.size() * sizeof(__half);
+  CFB_CUDA(cudaMalloc(&out.w, out.bytes));
+  CFB_CUDA(cudaMemcpy(out.w, buf.data(), out.bytes, cudaMemcpyHostToDevice));
+  CFB_CUDA(cudaMalloc(&out.bias, 16 * sizeof(float)));
+  CFB_CUDA(cudaMemcpy(out.bias, h_bias, 16 * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+void launch_first_conv_umma(const void* chunk_u8, Int3 cs, const PatchPos* patches, int nb, Int3 ps, const PackedConv& w,
+                            __half* out, cudaStream_t s) {
+  FirstConvParams p{};
+  p.chunk = static_cast<const uint8_t*>(chunk_u8); p.cs = cs; p.patches = patches; p.ps = ps;
+  p.wpacked = w.w; p.bias = w.bias; p.out = out;
+  p.tiles_x = ceil_div(ps.x, 128);
+  p.total_tiles = nb * ps.z * ps.y * p.tiles_x;
+  const int grid = std::min<int>(p.total_tiles, 2 * sm_count());
+  if (w.parts == 2) first_conv_umma_kernel<true><<<grid, kFcThreads, 0, s>>>(p);
+  else first_conv_umma_kernel<false><<<grid, kFcThreads, 0, s>>>(p);
+  CFB_LAUNCH_CHECK();
 }
 
 void free_packed(PackedConv& p) {

@@ -65,6 +65,14 @@ void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, c
 void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out);
 void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int nb, Int3 in_size, cudaStream_t s);
 
+// First layer (Cin = 1 -> 16) on tcgen05, fused with uint8 patch extraction (+ /255, bias, ReLU -> CP8).
+// EXPERIMENTAL (env CFB_UMMA_FIRST_CONV=1): correct, but the per-thread im2col gather is latency-bound
+// (27.7 ms vs 7.8 ms per 99 patches for the CUDA-core kernel), so the CUDA-core kernel stays the default.
+// h_w: (16, 1, 3, 3, 3) fp32.
+void pack_first_conv_weights(const float* h_w, const float* h_bias, int parts, PackedConv& out);
+void launch_first_conv_umma(const void* chunk_u8, Int3 chunk_size, const PatchPos* patches, int nb, Int3 patch,
+                            const PackedConv& w, __half* out, cudaStream_t s);
+
 // Layout conversion (tests / debug): planar fp32 (nb, C, Z,Y,X) <-> CP8.
 void launch_planar_to_cp8(const float* in, __half* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
 void launch_cp8_to_planar(const __half* in, float* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);

@@ -343,3 +343,27 @@ def test_device_test_time_augmentation(unet_model, precision):
     print("device TTA max-abs", precision, err, "| TTA changes the result by", np.abs(o - plain).max())
     assert err <= (NET_ATOL_F32 if precision == "f16x3" else NET_ATOL_SIMT)
     assert np.abs(o - plain).max() > 1e-2   # the augmentation is not a no-op for a real network
+
+
+def test_kernel_variants_agree(monkeypatch, unet_model):
+    """Every tcgen05 kernel variant computes the same network: fused vs unfused tail, CUDA-core vs (experimental, latency-bound) tensor-core
+    first layer, tensor-core vs CUDA-core transposed convolutions, z-stacked vs per-tap 3x3x3 kernel (forced through env switches)."""
+    rng = np.random.default_rng(31)
+    img = rng.integers(0, 256, size=(20, 96, 104), dtype=np.uint8)
+    kw = dict(input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3, framework="b200",
+              batch_size=5)
+    ref, _ = O.infer_chunk(img, input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3,
+                           framework="pytorch", model=unet_model)
+    results = {}
+    for name, env in [("default", {}), ("unfused_tail", {"CFB_NO_FUSED_TAIL": "1"}), ("umma_first", {"CFB_UMMA_FIRST_CONV": "1"}),
+                      ("simt_convT", {"CFB_SIMT_CONVT": "1"}), ("per_tap", {"CFB_NO_ZSTACK": "1"}), ("zstack4", {"CFB_FORCE_ZSTACK": "4"})]:
+        for k in ("CFB_NO_FUSED_TAIL", "CFB_UMMA_FIRST_CONV", "CFB_SIMT_CONVT", "CFB_NO_ZSTACK", "CFB_FORCE_ZSTACK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        results[name] = _inferencer(model=MODEL_FILE, **kw)(Chunk(img)).array
+        err = np.abs(results[name] - ref).max()
+        print(name, "max-abs vs oracle", err)
+        assert err <= NET_ATOL_F32, name
+    for name, arr in results.items():
+        assert np.abs(arr - results["default"]).max() <= 5e-5, name

@@ -122,7 +122,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CFB_BENCH_WORKLOAD", "1024"), choices=sorted(WORKLOADS))
-    ap.add_argument("--batch-size", type=int, default=int(os.environ.get("CFB_BENCH_BATCH", 8)))
+    ap.add_argument("--batch-size", type=int, default=int(os.environ.get("CFB_BENCH_BATCH", 12)))
     ap.add_argument("--precision", default=os.environ.get("CHUNKFLOW_B200_PRECISION"))
     ap.add_argument("--cpu-sample-patches", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -20,7 +20,7 @@ DTYPE_U8, DTYPE_F32 = 0, 1
 
 # every symbol include/chunkflow_b200.h declares
 EXPORTS = (
-    "cfb_last_error", "cfb_version", "cfb_device_count", "cfb_create", "cfb_destroy", "cfb_device_name",
+    "cfb_last_error", "cfb_version", "cfb_device_count", "cfb_device_memory", "cfb_create", "cfb_destroy", "cfb_device_name",
     "cfb_set_weight", "cfb_commit_weights", "cfb_patch_mask", "cfb_patch_grid", "cfb_output_shape",
     "cfb_infer_chunk_device", "cfb_infer_chunk_host", "cfb_infer_slab_device", "cfb_normalize_device",
     "cfb_patch_forward_host", "cfb_make_patch_mask", "cfb_plugin_begin", "cfb_plugin_extract", "cfb_plugin_blend",
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.cfb_device_name.argtypes = [vp]
     lib.cfb_version.restype = C.c_int
     lib.cfb_device_count.restype = C.c_int
+    lib.cfb_device_memory.argtypes = [i32, C.POINTER(i64), C.POINTER(i64)]
     lib.cfb_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
     lib.cfb_destroy.argtypes = [vp]
     lib.cfb_set_weight.argtypes = [vp, C.c_char_p, vp, i64]
@@ -111,6 +112,13 @@ def check(code: int) -> None:
 
 def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
+
+
+def device_memory(device: int = 0) -> tuple:
+    """(free, total) bytes of device memory."""
+    f, t = C.c_int64(), C.c_int64()
+    check(load().cfb_device_memory(int(device), C.byref(f), C.byref(t)))
+    return f.value, t.value
 
 
 def make_patch_mask(patch_size, overlap) -> np.ndarray:

@@ -373,6 +373,18 @@ int cfb_device_count(void) {
   return n;
 }
 
+int cfb_device_memory(int32_t device, int64_t* free_bytes, int64_t* total_bytes) {
+  return guarded([&]() -> int {
+    if (!free_bytes || !total_bytes) throw std::invalid_argument("null argument");
+    if (cfb_device_count() <= 0) { set_last_error("no CUDA device available: chunkflow_b200 has no CPU fallback"); return CFB_ERR_CUDA; }
+    CFB_CUDA(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    CFB_CUDA(cudaMemGetInfo(&f, &t));
+    *free_bytes = (int64_t)f; *total_bytes = (int64_t)t;
+    return CFB_OK;
+  });
+}
+
 int cfb_create(const cfb_params* params, cfb_handle* out) {
   return guarded([&]() -> int {
     if (!params || !out) throw std::invalid_argument("null argument");

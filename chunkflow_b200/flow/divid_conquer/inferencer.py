@@ -139,7 +139,7 @@ class Inferencer(object):
             output_crop_margin=self.output_crop_margin,
             num_input_channels=self.num_input_channels,
             num_output_channels=self.num_output_channels,
-            batch_size=self.batch_size,
+            batch_size=self._patches_in_flight(framework_code),
             mask_output_chunk=self.mask_output_chunk,
             framework=framework_code,
             precision=b200_patch.precision_code(self.dtype, precision),
@@ -147,6 +147,17 @@ class Inferencer(object):
             mask_myelin_threshold=self.mask_myelin_threshold,
             augment=augment,
             check_output_range=True)
+
+    def _patches_in_flight(self, framework_code) -> int:
+        """``batch_size`` is a scheduling hint here (the reference asserts 1 for pytorch although its examples pass
+        12, inferencer.py:216-220).  With the default of 1 the device network path picks the number of patches in
+        flight itself: enough CTAs to fill 148 SMs at every U-Net level, bounded by a quarter of the free memory
+        (about 540 bytes of fp16 hi/lo activations per patch voxel)."""
+        if self.batch_size > 1 or framework_code != _native.FRAMEWORK_UNET3L:
+            return self.batch_size
+        free, _ = _native.device_memory(self.device)
+        per_patch = int(np.prod(self.input_patch_size)) * 600
+        return int(max(1, min(12, (free // 4) // max(per_patch, 1))))
 
     def _prepare_patch_inferencer(self, framework, convnet_model, convnet_weight_path, bump, precision):
         self.patch_inferencer = None   # host-side per-patch plugin (universal / prebuilt) if any

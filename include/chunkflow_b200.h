@@ -82,6 +82,9 @@ int cfb_version(void);
 /* Number of CUDA devices visible (0 if none / no driver). Never fails. */
 int cfb_device_count(void);
 
+/* Free / total bytes of device memory (used to size the number of patches in flight). */
+int cfb_device_memory(int32_t device, int64_t* free_bytes, int64_t* total_bytes);
+
 int cfb_create(const cfb_params* params, cfb_handle* out);
 int cfb_destroy(cfb_handle h);
 /* Name of the CUDA device the engine runs on (valid until cfb_destroy). */

@@ -201,11 +201,16 @@ def main():
     if sampler:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ncu_range = bool(os.environ.get("CFB_NCU_RANGE"))  # `ncu --profile-from-start off`: capture the timed region only
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     torch.cuda.synchronize()
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if sampler else None

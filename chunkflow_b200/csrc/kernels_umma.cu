@@ -137,6 +137,27 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&r)[16])
       "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y),
+               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+// rows of a TMEM matrix move one lane down (lane i <- lane i+1) inside every 32-lane group; 32-byte elements
+__device__ __forceinline__ void tc_shift_down(uint32_t taddr) {
+  asm volatile("tcgen05.shift.cta_group::1.down [%0];" ::"r"(taddr) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_f16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor), 64 bits:
@@ -227,6 +248,7 @@ struct UmmaConvParams {
   const __half* wpacked_zs;  // z-stacked weight blocks
   FusedTail tail;  // used by the TAIL = true instantiations only
   int total_items; // z-stacked kernel: work items = batch x tiles x z blocks (persistent CTAs)
+  const __half* wpacked_ts;  // TMEM-shift kernel: (dy, kg) triples of z-stacked blocks
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
@@ -737,6 +759,316 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------
+// z-stacked + TMEM-shift variant ("TS"): the dx taps re-use one TMEM-resident activation tile.
+//
+// On top of the z-stacking above, the A operand of the MMAs comes from TENSOR MEMORY: four loader warps
+// copy the 128-position tile of one (input plane, dy, K step, hi/lo part) from the shared-memory plane
+// into an 8-column TMEM buffer (row = lane, K = 16 fp16 = 8 packed columns; tcgen05.st), and the single
+// MMA thread issues   MMA(dx=0) ; tcgen05.shift.down ; MMA(dx=1) ; tcgen05.shift.down ; MMA(dx=2)
+// back to back -- the shift moves row i+1 into lane i inside every 32-lane group (measured with
+// tools/probes/probe_tmem.cu: executes in issue order with the MMAs; the last lane of a group keeps its
+// value), i.e. the dx = +1 tap.  A tile is thus read from shared memory ONCE per (dy, K step, part) by
+// ordinary ld.shared instead of three times by the tensor core's operand fetch, which was the limiter.
+// Because two lanes per 32-lane group go stale, an M tile carries 4 x 30 = 120 valid positions:
+// lane (k, i) <-> position 120 g + 30 k + i, i < 30 valid.
+// Weight blocks: (dy, kg) triples of the z-stacked blocks of dx = 0, 1, 2.
+// ------------------------------------------------------------------------------------------
+constexpr int kThreadsTS = 352;   // 11 warps: A producer, B producer, MMA, 4 epilogue, 4 TMEM loaders
+constexpr int kTsABufs = 8;       // TMEM A-tile ring (8 columns each) at columns [448, 512)
+constexpr int kTsACol0 = 448;
+constexpr int kTsAccCols = 224;   // accumulator columns per buffer (2 buffers)
+constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsABufs) * 8 + 16 + 640;
+
+template <int CIN, int COUT, bool SPLIT, bool TAIL>
+__global__ void __launch_bounds__(kThreadsTS, 1)
+conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                     const UmmaConvParams p) {
+  using Cfg = ConvCfg<CIN, COUT, SPLIT>;
+  constexpr int P = Cfg::P;
+  constexpr int NB = Cfg::NB;
+  constexpr int BSTAGE = 9 * Cfg::BSTAGE;  // (dy, kg) triple: dx = 0,1,2, each with three dz row groups
+  constexpr int KSTEPS = CIN / 16;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int njobs = (p.Z + p.T - 1) / p.T;
+  const int ncols = p.tiles_x * p.tiles_y;
+  struct Item { int b, x0, y0, z0; };
+  auto item_of = [&](int item) {
+    const int j = item % njobs, col = item / njobs;
+    return Item{col / ncols, (col % p.tiles_x) * p.XT, ((col / p.tiles_x) % p.tiles_y) * p.TY, j * p.T};
+  };
+
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kRing * p.slot_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.bstages * BSTAGE);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int kBF = 10, kBE = 10 + kMaxBStages, kAccF = 6, kAccE = 8;
+  constexpr int kTF = 10 + 2 * kMaxBStages, kTE = kTF + kTsABufs;  // TMEM A tile full / empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTE + kTsABufs);
+  float* s_head = reinterpret_cast<float*>(bars + kTE + kTsABufs + 2);
+  PatchPos pp{};
+  if constexpr (TAIL) {
+    for (int i = threadIdx.x; i < p.tail.channels * 16; i += kThreadsTS) s_head[i] = p.tail.head_w[i];
+    for (int i = threadIdx.x; i < p.tail.channels; i += kThreadsTS) s_head[p.tail.channels * 16 + i] = p.tail.head_b[i];
+  }
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+    for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), 1); mbar_init(BAR(kAccE + i), 128); }
+    for (int i = 0; i < kTsABufs; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), 1); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int Z = p.Z, T = p.T;
+
+  if (warp == 0) {
+    // ---------------- A producer (TMA z-plane ring), as in the z-stacked kernel ----------------
+    if (elect_one()) {
+      const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
+      int slot = 0, ld = 0;
+      uint32_t prev_parity = 1;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const Item it = item_of(item);
+        const int x0 = it.x0, y0 = it.y0, z0 = it.z0;
+        const int plane_a0 = it.b * p.planes_a * P, plane_b0 = it.b * p.planes_b * P;
+        const int qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+        for (int q = qlo; q <= qhi; ++q, ++ld) {
+          if (ld >= kRing) mbar_wait(BAR(3 + slot), prev_parity);
+          mbar_expect_tx(BAR(slot), tx_bytes);
+          const uint32_t dst = smem_u32(sA + (size_t)slot * p.slot_stride);
+          const uint32_t dst_b = dst + (uint32_t)(p.planes_a * P) * p.plane_stride;
+          if (p.wide_map) {
+            tma_load_5d(dst, &mapA, BAR(slot), 0, x0 - 1, y0 - 1, q, plane_a0);
+            if (p.planes_b > 0) tma_load_5d(dst_b, &mapB, BAR(slot), 0, x0 - 1, y0 - 1, q, plane_b0);
+          } else {
+            tma_load_4d(dst, &mapA, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_a0);
+            if (p.planes_b > 0) tma_load_4d(dst_b, &mapB, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_b0);
+          }
+          if (++slot == kRing) { slot = 0; prev_parity ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- B producer: 3 * KG (dy, kg) triples per input plane ----------------
+    if (elect_one()) {
+      const uint32_t per_plane = 3u * Cfg::KG;
+      const uint32_t nbs = (uint32_t)p.bstages;
+      uint32_t planes = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int z0 = item_of(item).z0;
+        planes += (uint32_t)(min(z0 + T, Z - 1) - max(z0 - 1, 0) + 1);
+      }
+      const uint32_t total = p.bresident ? per_plane : planes * per_plane;
+      uint32_t st = 0, blk = 0, prev_parity = 1;
+      for (uint32_t i = 0; i < total; ++i) {
+        if (i >= nbs) mbar_wait(BAR(kBE + st), prev_parity);
+        mbar_expect_tx(BAR(kBF + st), BSTAGE);
+        for (int part = 0; part < 9; ++part)  // bulk copies of at most one per-tap block each
+          bulk_load(smem_u32(sB + st * BSTAGE + part * Cfg::BSTAGE),
+                    reinterpret_cast<const uint8_t*>(p.wpacked_ts) + (size_t)blk * BSTAGE + (size_t)part * Cfg::BSTAGE,
+                    Cfg::BSTAGE, BAR(kBF + st));
+        if (++st == nbs) { st = 0; prev_parity ^= 1; }
+        if (++blk == per_plane) blk = 0;
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer ----------------
+    if (elect_one()) {
+      constexpr uint32_t DESC_HI = 8u | (1u << 14);
+      constexpr uint32_t b_lbo = (uint32_t)(3 * NB) << 16;
+      const uint32_t sB16 = smem_u32(sB) >> 4;
+      const uint32_t G = (uint32_t)p.G;
+      const bool resident = p.bresident != 0;
+      const uint32_t nbs = (uint32_t)p.bstages;
+      auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
+      uint32_t ring_st = 0, ring_parity = 0;
+      uint32_t slot = 0;
+      uint32_t tbuf = 0, tparity = 0;  // TMEM A-tile ring position
+      bool first_plane = true;
+      int jj = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
+        const uint32_t buf = (uint32_t)jj & 1u;
+        mbar_wait(BAR(kAccE + buf), (uint32_t)(jj >> 1) & 1u);
+        tc_fence_after();
+        const int z0 = item_of(item).z0, z1 = min(z0 + T, Z), qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+        const uint32_t dbuf = tmem_base + buf * kTsAccCols;
+        for (int q = qlo; q <= qhi; ++q) {
+          const int plo = max(q - 1, z0), phi = min(q + 1, z1 - 1);
+          const uint32_t ng = (uint32_t)(phi - plo + 1);
+          const uint32_t row0 = (uint32_t)(2 - (q - plo + 1)) * NB;
+          const uint32_t idesc = make_idesc((int)(ng * NB));
+          const uint32_t dcol0 = dbuf + (uint32_t)(plo - z0) * NB;
+          uint32_t blk = 0;
+          for (int dy = 0; dy < 3; ++dy) {
+            for (int kg = 0; kg < Cfg::KG; ++kg) {
+              uint32_t b16;
+              if (resident) {
+                if (first_plane) { mbar_wait(BAR(kBF + blk), 0); tc_fence_after(); }
+                b16 = sB16 + blk * (BSTAGE >> 4);
+                ++blk;
+              } else {
+                mbar_wait(BAR(kBF + ring_st), ring_parity);
+                tc_fence_after();
+                b16 = sB16 + ring_st * (BSTAGE >> 4);
+              }
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KS; ++ks) {
+                const uint32_t bk = b16 + (uint32_t)ks * 2u * (3 * NB) + row0;
+                for (int part = 0; part < P; ++part) {
+                  uint32_t d = dcol0;
+                  for (uint32_t g = 0; g < G; ++g, d += (uint32_t)T * NB) {
+                    mbar_wait(BAR(kTF + tbuf), tparity);  // loader warps filled this TMEM A tile
+                    tc_fence_after();
+                    const uint32_t a_tm = tmem_base + kTsACol0 + tbuf * 8;
+#pragma unroll
+                    for (uint32_t dx = 0; dx < 3; ++dx) {
+                      if (dx) tc_shift_down(a_tm);
+                      tc_mma_f16_ta(d, a_tm, desc(b_lbo | (bk + dx * (3 * Cfg::BSTAGE >> 4))), idesc, 1u);
+                    }
+                    tc_commit(BAR(kTE + tbuf));
+                    if (++tbuf == kTsABufs) { tbuf = 0; tparity ^= 1; }
+                  }
+                }
+              }
+              if (!resident) {
+                tc_commit(BAR(kBE + ring_st));
+                if (++ring_st == nbs) { ring_st = 0; ring_parity ^= 1; }
+              }
+            }
+          }
+          first_plane = false;
+          tc_commit(BAR(3 + slot));  // every MMA that depended on this shared-memory plane has completed
+          if (++slot == kRing) slot = 0;
+        }
+        tc_commit(BAR(kAccF + buf));
+      }
+    }
+  } else if (warp >= 7) {
+    // ---------------- TMEM loaders: shared-memory plane -> A tile in tensor memory ----------------
+    const int wq = warp & 3;                    // lane quarter this warp may access
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    const uint32_t pos_in_tile = (uint32_t)(30 * wq + lane);  // lane (k, i) <-> position 30 k + i
+    const uint32_t plane16 = p.plane_stride >> 4;
+    const uint4* sA16 = reinterpret_cast<const uint4*>(sA);
+    uint32_t slot = 0, sparity = 0;
+    uint32_t tbuf = 0, tparity = 1;  // parity of the previous release (none during the first round)
+    uint32_t tcount = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int z0 = item_of(item).z0, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
+      for (int q = qlo; q <= qhi; ++q) {
+        mbar_wait(BAR(slot), sparity);  // TMA has landed this z-plane
+        const uint4* plane = sA16 + (size_t)slot * (p.slot_stride >> 4);
+        for (int dy = 0; dy < 3; ++dy) {
+          for (int kstep = 0; kstep < KSTEPS; ++kstep) {
+            for (int part = 0; part < P; ++part) {
+              const uint4* src = plane + (size_t)((kstep * 2) * P + part) * plane16 + dy * p.pitch + pos_in_tile;
+              for (int g = 0; g < p.G; ++g, ++tcount) {
+                if (tcount >= kTsABufs) mbar_wait(BAR(kTE + tbuf), tparity);
+                tc_fence_after();
+                const uint4 c0 = src[g * 120], c1 = src[(size_t)P * plane16 + g * 120];
+                tc_st8(tmem_base + lane_base + kTsACol0 + tbuf * 8, c0, c1);
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(BAR(kTF + tbuf));
+                if (++tbuf == kTsABufs) { tbuf = 0; tparity ^= 1; }
+              }
+            }
+          }
+        }
+        if (++slot == kRing) { slot = 0; sparity ^= 1; }
+      }
+    }
+  } else {
+    // ---------------- epilogue (warps 3..6) ----------------
+    const int wq = warp & 3;
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    {
+      const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 2 * kTsAccCols; c += 16) tc_st16(tmem_base + lane_base + c, zero);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR(kAccE + 0));
+      mbar_arrive(BAR(kAccE + 1));
+    }
+    const size_t plane_vox = (size_t)p.Z * p.Y * p.X;
+    const float inv_pitch = 1.0f / (float)p.pitch;
+    uint4* out16 = reinterpret_cast<uint4*>(p.out);
+    int jj = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
+      const int buf = jj & 1;
+      const Item it = item_of(item);
+      const int b = it.b, x0 = it.x0, y0 = it.y0, z0 = it.z0, z1 = min(z0 + T, Z);
+      const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
+      if constexpr (TAIL) pp = p.tail.patches[b];
+      mbar_wait(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u);
+      tc_fence_after();
+      for (int g = 0; g < p.G; ++g) {
+        const int qpos = g * 120 + 30 * wq + lane;
+        const int row = __float2int_rd(((float)qpos + 0.5f) * inv_pitch), col = qpos - row * p.pitch;
+        const bool valid = lane < 30 && row < ty_valid && col < xt_valid;
+        for (int pz = z0; pz < z1; ++pz) {
+          const size_t vox = ((size_t)pz * p.Y + (y0 + row)) * p.X + (x0 + col);
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTsAccCols + (g * T + (pz - z0)) * NB);
+#pragma unroll
+          for (int cb = 0; cb < COUT / 16; ++cb) {
+            uint32_t r[16];
+            tc_ld16(taddr + cb * 16, r);
+            float v[16];
+            if (SPLIT) {
+              uint32_t r2[16];
+              tc_ld16(taddr + COUT + cb * 16, r2);
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
+            } else {
+              tc_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[i] += __ldg(p.bias + cb * 16 + i);
+              if (p.relu) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (valid) {
+              if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, pz, y0 + row, x0 + col);
+              else store_cp8_16<COUT, SPLIT>(v, cb, b, vox, plane_vox, out16);
+            }
+          }
+          {
+            const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < NB; c += 16) tc_st16(taddr + c, zero);
+          }
+        }
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR(kAccE + buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Transposed convolution kernel = stride = (1,2,2) on tcgen05: a plain GEMM per input voxel,
 //   D[voxel, (tap, cout)] = sum_ci A[voxel, ci] * W[ci, cout, tap],   tap = (a, b) in {0,1}^2,
 // followed by a scatter epilogue: tap (a, b) of input voxel (z, y, x) is output voxel
@@ -1208,10 +1540,40 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
       }
     }
   }
+  // z-stacked + TMEM-shift variants: M tiles of 120 positions, accumulators G * T * NB <= 224 columns per buffer
+  if (3 * Cfg::NB <= 256 && !getenv("CFB_NO_TSHIFT") && !getenv("CFB_NO_ZSTACK")) {
+    for (auto& e : xts) {
+      const int XT = e.first, pitch = XT + 2;
+      for (int T : {2, 3, 4, 6}) {
+        if (T > sz.z && T != 2) continue;
+        for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
+          const size_t plane = (size_t)(tyc + 2) * pitch * 16;
+          const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
+          const int G = ceil_div(tyc * pitch, 120);
+          if (G * T * Cfg::NB > kTsAccCols || slot >= (1u << 18)) continue;
+          const size_t fixed = (size_t)kTsBarBytes + kTailPad + 128;
+          if ((size_t)kRing * slot + fixed >= (size_t)kMaxSmem) continue;
+          const size_t room = (size_t)kMaxSmem - (size_t)kRing * slot - fixed;
+          const int all_blocks = 3 * Cfg::KG;
+          const int bstage = 9 * Cfg::BSTAGE;
+          int bs = (int)std::min<size_t>(room / bstage, kMaxBStages);
+          if (bs >= all_blocks) bs = all_blocks;
+          if (bs < 2) continue;
+          ConvTile t;
+          t.T = T; t.shift = true; t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
+          const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
+          // tensor/B-bound rather than tile-read bound: about half the z-stacked kernel's cost per position
+          t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T)) * 0.6);
+          out.push_back(t);
+        }
+      }
+    }
+  }
   if (const char* force = getenv("CFB_FORCE_ZSTACK")) {  // tests: exercise one kernel variant only
     const int T = atoi(force);
+    const bool want_shift = getenv("CFB_FORCE_TSHIFT") != nullptr;
     std::vector<ConvTile> only;
-    for (const ConvTile& t : out) if (t.T == T) only.push_back(t);
+    for (const ConvTile& t : out) if (t.T == T && t.shift == want_shift) only.push_back(t);
     if (!only.empty()) out.swap(only);
   }
   std::sort(out.begin(), out.end(), [](const ConvTile& a, const ConvTile& b) { return a.cost < b.cost; });
@@ -1235,15 +1597,15 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   p.bstages = t.bstages;
   p.bresident = t.resident ? 1 : 0;
   p.wide_map = t.wide ? 1 : 0;
-  p.G = row_aligned ? p.TY : ceil_div(p.TY * p.pitch, 128);
+  p.G = t.shift ? ceil_div(p.TY * p.pitch, 120) : (row_aligned ? p.TY : ceil_div(p.TY * p.pitch, 128));
   p.tiles_y = ceil_div(sz.y, p.TY);
   p.plane_stride = (uint32_t)((p.TY + 2) * p.pitch * 16);
   p.slot_stride = (uint32_t)((Cfg::NPL * (size_t)p.plane_stride + 127) / 128 * 128);
   p.planes_a = ca / 8; p.planes_b = cb / 8;
-  p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
+  p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.wpacked_ts = w.w_ts; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
   p.T = t.T;
-  const size_t bstage = t.T ? 3 * (size_t)Cfg::BSTAGE : (size_t)Cfg::BSTAGE;
-  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + kBarBytes + kTailPad + 128;
+  const size_t bstage = t.shift ? 9 * (size_t)Cfg::BSTAGE : (t.T ? 3 * (size_t)Cfg::BSTAGE : (size_t)Cfg::BSTAGE);
+  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + (t.shift ? kTsBarBytes : kBarBytes) + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
   int grid = nb * p.tiles_x * p.tiles_y;
@@ -1251,15 +1613,16 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
     p.total_items = grid * ceil_div(sz.z, t.T);
     grid = std::min<int>(p.total_items, sm_count());
   }
-  auto run = [&](auto kern) {
+  auto run = [&](auto kern, int threads = kThreads) {
     CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, s>>>(mapA, mapB, p);
+    kern<<<grid, threads, smem, s>>>(mapA, mapB, p);
     CFB_LAUNCH_CHECK();
   };
   if (tail) {
     if constexpr (CIN == 16 && COUT == 16) {
       p.tail = *tail;
-      if (t.T) run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, true>);
+      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, true>, kThreadsTS);
+      else if (t.T) run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, true>);
       else run(conv3_umma_kernel<CIN, COUT, SPLIT, true>);
       return;
     } else {
@@ -1268,7 +1631,8 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   }
   if (t.T) {
     if constexpr (3 * Cfg::NB <= 256) {
-      run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, false>);
+      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false>, kThreadsTS);
+      else run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, false>);
       return;
     } else {
       throw std::runtime_error("z-stacked kernel needs 3 * NB <= 256");
@@ -1305,7 +1669,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       CFB_CUDA(cudaEventCreate(&e0));
       CFB_CUDA(cudaEventCreate(&e1));
       float best_ms = 1e30f;
-      const size_t n = std::min<size_t>(cands.size(), 32);
+      const size_t n = std::min<size_t>(cands.size(), 40);
       for (size_t i = 0; i < n; ++i) {
         launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
         CFB_CUDA(cudaEventRecord(e0, s));
@@ -1321,8 +1685,8 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       best.cost = best_ms;
     }
     if (getenv("CFB_DEBUG_CFG"))
-      fprintf(stderr, "[cfb] conv3 %d->%d split=%d size=%dx%dx%d nb=%d: zstack T=%d XT=%d%s TY=%d bstages=%d resident=%d (%s %.3f)\n",
-              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.T, best.XT, best.wide ? "w" : "", best.TY, best.bstages,
+      fprintf(stderr, "[cfb] conv3 %d->%d split=%d size=%dx%dx%d nb=%d: zstack T=%d%s XT=%d%s TY=%d bstages=%d resident=%d (%s %.3f)\n",
+              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.T, best.shift ? "+shift" : "", best.XT, best.wide ? "w" : "", best.TY, best.bstages,
               (int)best.resident, tune ? "tuned ms" : "model cost", best.cost);
     it = w.tuned->emplace(key, best).first;
   }
@@ -1431,6 +1795,16 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
             }
   CFB_CUDA(cudaMalloc(&out.w_zs, zs.size() * sizeof(__half)));
   CFB_CUDA(cudaMemcpy(out.w_zs, zs.data(), zs.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  // TMEM-shift kernel: the same blocks ordered (dy, kg, dx)
+  std::vector<__half> ts(zs.size());
+  for (int dy = 0; dy < 3; ++dy)
+    for (int g = 0; g < KG; ++g)
+      for (int dx = 0; dx < 3; ++dx)
+        std::copy(zs.begin() + ((size_t)(dy * 3 + dx) * KG + g) * (3 * block),
+                  zs.begin() + ((size_t)(dy * 3 + dx) * KG + g + 1) * (3 * block),
+                  ts.begin() + (((size_t)dy * KG + g) * 3 + dx) * (3 * block));
+  CFB_CUDA(cudaMalloc(&out.w_ts, ts.size() * sizeof(__half)));
+  CFB_CUDA(cudaMemcpy(out.w_ts, ts.data(), ts.size() * sizeof(__half), cudaMemcpyHostToDevice));
 }
 
 void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int nb, Int3 in_size, cudaStream_t s) {
@@ -1505,6 +1879,7 @@ void launch_first_conv_umma(const void* chunk_u8, Int3 cs, const PatchPos* patch
 void free_packed(PackedConv& p) {
   if (p.w) cudaFree(p.w);
   if (p.w_zs) cudaFree(p.w_zs);
+  if (p.w_ts) cudaFree(p.w_ts);
   if (p.bias) cudaFree(p.bias);
   p = PackedConv{};
 }

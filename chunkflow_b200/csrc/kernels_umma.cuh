@@ -27,6 +27,7 @@ namespace cfb {
 struct ConvTile {
   int XT = 0, TY = 0, bstages = 0;
   int T = 0;  // > 0: z-stacked kernel with T output planes per job
+  bool shift = false;  // z-stacked + TMEM-resident activation tile with tcgen05.shift for the dx taps
   bool resident = false, wide = false;
   double cost = 0.0;
 };
@@ -34,6 +35,7 @@ struct ConvTile {
 struct PackedConv {
   __half* w = nullptr;     // device, per-tap blocks
   __half* w_zs = nullptr;  // device, z-stacked blocks (3x3x3 layers only)
+  __half* w_ts = nullptr;  // device, (dy, kg) triples of z-stacked blocks for the TMEM-shift kernel
   float* bias = nullptr;
   int cin = 0, cout = 0, parts = 1;
   size_t bytes = 0;

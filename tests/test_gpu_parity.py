@@ -166,6 +166,18 @@ def test_conv3_layer_tcgen05_zstacked_kernel(monkeypatch, zstack, cin, cout, siz
         _conv3_case(_native.PRECISION_F16_UMMA, cin, cout, size, 1e-2)
 
 
+@pytest.mark.parametrize("zstack", ["2", "3", "4"])
+@pytest.mark.parametrize("cin,cout,size", [(16, 16, (3, 8, 40)), (16, 16, (9, 16, 70)), (32, 32, (5, 12, 20)), (16, 32, (4, 6, 128)),
+                                           (32, 16, (7, 8, 130)), (64, 32, (4, 16, 16)), (16, 16, (1, 7, 9))])
+def test_conv3_layer_tcgen05_tmem_shift_kernel(monkeypatch, zstack, cin, cout, size):
+    """z-stacked + TMEM-resident activation tile: MMA(dx=0), tcgen05.shift, MMA(dx=1), shift, MMA(dx=2)."""
+    monkeypatch.setenv("CFB_FORCE_ZSTACK", zstack)
+    monkeypatch.setenv("CFB_FORCE_TSHIFT", "1")
+    _conv3_case(_native.PRECISION_F16X3_UMMA, cin, cout, size, 5e-5)
+    if cin == 16:
+        _conv3_case(_native.PRECISION_F16_UMMA, cin, cout, size, 1e-2)
+
+
 @pytest.mark.parametrize("cin,cout,size", UMMA_CASES[:4])
 def test_conv3_layer_tcgen05_fp16_against_torch(cin, cout, size):
     # single-pass fp16: 11-bit operands and 11-bit stored outputs on values of magnitude ~5
@@ -356,8 +368,10 @@ def test_kernel_variants_agree(monkeypatch, unet_model):
                            framework="pytorch", model=unet_model)
     results = {}
     for name, env in [("default", {}), ("unfused_tail", {"CFB_NO_FUSED_TAIL": "1"}), ("umma_first", {"CFB_UMMA_FIRST_CONV": "1"}),
-                      ("simt_convT", {"CFB_SIMT_CONVT": "1"}), ("per_tap", {"CFB_NO_ZSTACK": "1"}), ("zstack4", {"CFB_FORCE_ZSTACK": "4"})]:
-        for k in ("CFB_NO_FUSED_TAIL", "CFB_UMMA_FIRST_CONV", "CFB_SIMT_CONVT", "CFB_NO_ZSTACK", "CFB_FORCE_ZSTACK"):
+                      ("simt_convT", {"CFB_SIMT_CONVT": "1"}), ("per_tap", {"CFB_NO_ZSTACK": "1"}), ("zstack4", {"CFB_FORCE_ZSTACK": "4"}),
+                      ("no_shift", {"CFB_NO_TSHIFT": "1"}), ("shift2", {"CFB_FORCE_ZSTACK": "2", "CFB_FORCE_TSHIFT": "1"})]:
+        for k in ("CFB_NO_FUSED_TAIL", "CFB_UMMA_FIRST_CONV", "CFB_SIMT_CONVT", "CFB_NO_ZSTACK", "CFB_FORCE_ZSTACK", "CFB_NO_TSHIFT",
+                  "CFB_FORCE_TSHIFT"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

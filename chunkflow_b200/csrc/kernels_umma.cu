@@ -774,10 +774,11 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 // Weight blocks: (dy, kg) triples of the z-stacked blocks of dx = 0, 1, 2.
 // ------------------------------------------------------------------------------------------
 constexpr int kThreadsTS = 352;   // 11 warps: A producer, B producer, MMA, 4 epilogue, 4 TMEM loaders
-constexpr int kTsABufs = 8;       // TMEM A-tile ring (8 columns each) at columns [448, 512)
-constexpr int kTsACol0 = 448;
-constexpr int kTsAccCols = 224;   // accumulator columns per buffer (2 buffers)
-constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsABufs) * 8 + 16 + 640;
+constexpr int kTsGroups = 2;      // ring of A-tile GROUPS in TMEM; a group = all (part, tile) A tiles of one (plane, dy, K step)
+constexpr int kTsMaxTiles = 8;    // P * G <= 8 tiles of 8 columns per group
+constexpr int kTsACol0 = 384;     // groups live at columns [384, 512)
+constexpr int kTsAccCols = 192;   // accumulator columns per buffer (2 buffers)
+constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsGroups) * 8 + 16 + 640;
 
 template <int CIN, int COUT, bool SPLIT, bool TAIL>
 __global__ void __launch_bounds__(kThreadsTS, 1)
@@ -786,7 +787,10 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
   constexpr int P = Cfg::P;
   constexpr int NB = Cfg::NB;
-  constexpr int BSTAGE = 9 * Cfg::BSTAGE;  // (dy, kg) triple: dx = 0,1,2, each with three dz row groups
+  constexpr int BSTAGE = 9 * Cfg::BSTAGE;  // (dy, kg) triple: dx = 0,1,2; block rows = [hi: dz 2,1,0 | lo: dz 2,1,0] x COUT
+  // With the A operand in tensor memory an extra pass over A is free, so hi/lo products are NOT concatenated
+  // along N here: a_hi x w_hi, a_hi x w_lo and a_lo x w_hi all accumulate into the same COUT columns of a plane
+  // (half the TMEM per plane -> twice the z-stacking depth T, fewer tensor cycles and fewer weight bytes per tap).
   constexpr int KSTEPS = CIN / 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -806,9 +810,9 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   constexpr int kBF = 10, kBE = 10 + kMaxBStages, kAccF = 6, kAccE = 8;
-  constexpr int kTF = 10 + 2 * kMaxBStages, kTE = kTF + kTsABufs;  // TMEM A tile full / empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTE + kTsABufs);
-  float* s_head = reinterpret_cast<float*>(bars + kTE + kTsABufs + 2);
+  constexpr int kTF = 10 + 2 * kMaxBStages, kTE = kTF + kTsGroups;  // TMEM A-tile group full / empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTE + kTsGroups);
+  float* s_head = reinterpret_cast<float*>(bars + kTE + kTsGroups + 2);
   PatchPos pp{};
   if constexpr (TAIL) {
     for (int i = threadIdx.x; i < p.tail.channels * 16; i += kThreadsTS) s_head[i] = p.tail.head_w[i];
@@ -819,7 +823,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
     for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), 1); mbar_init(BAR(kAccE + i), 128); }
-    for (int i = 0; i < kTsABufs; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), 1); }
+    for (int i = 0; i < kTsGroups; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), 1); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -895,7 +899,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
       uint32_t ring_st = 0, ring_parity = 0;
       uint32_t slot = 0;
-      uint32_t tbuf = 0, tparity = 0;  // TMEM A-tile ring position
+      uint32_t tgrp = 0, tparity = 0;  // TMEM A-tile group ring position
       bool first_plane = true;
       int jj = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
@@ -907,9 +911,9 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         for (int q = qlo; q <= qhi; ++q) {
           const int plo = max(q - 1, z0), phi = min(q + 1, z1 - 1);
           const uint32_t ng = (uint32_t)(phi - plo + 1);
-          const uint32_t row0 = (uint32_t)(2 - (q - plo + 1)) * NB;
-          const uint32_t idesc = make_idesc((int)(ng * NB));
-          const uint32_t dcol0 = dbuf + (uint32_t)(plo - z0) * NB;
+          const uint32_t row0 = (uint32_t)(2 - (q - plo + 1)) * COUT;  // first dz row group inside the hi (or lo) rows
+          const uint32_t idesc = make_idesc((int)(ng * COUT));
+          const uint32_t dcol0 = dbuf + (uint32_t)(plo - z0) * COUT;
           uint32_t blk = 0;
           for (int dy = 0; dy < 3; ++dy) {
             for (int kg = 0; kg < Cfg::KG; ++kg) {
@@ -926,21 +930,23 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
               for (int ks = 0; ks < Cfg::KS; ++ks) {
                 const uint32_t bk = b16 + (uint32_t)ks * 2u * (3 * NB) + row0;
-                for (int part = 0; part < P; ++part) {
+                mbar_wait(BAR(kTF + tgrp), tparity);  // the loader warps filled this group of TMEM A tiles
+                tc_fence_after();
+                uint32_t a_tm = tmem_base + kTsACol0 + tgrp * (kTsMaxTiles * 8);
+                for (int part = 0; part < P; ++part) {  // A tile part: 0 = hi, 1 = lo
                   uint32_t d = dcol0;
-                  for (uint32_t g = 0; g < G; ++g, d += (uint32_t)T * NB) {
-                    mbar_wait(BAR(kTF + tbuf), tparity);  // loader warps filled this TMEM A tile
-                    tc_fence_after();
-                    const uint32_t a_tm = tmem_base + kTsACol0 + tbuf * 8;
+                  for (uint32_t g = 0; g < G; ++g, d += (uint32_t)T * COUT, a_tm += 8) {
 #pragma unroll
                     for (uint32_t dx = 0; dx < 3; ++dx) {
                       if (dx) tc_shift_down(a_tm);
-                      tc_mma_f16_ta(d, a_tm, desc(b_lbo | (bk + dx * (3 * Cfg::BSTAGE >> 4))), idesc, 1u);
+                      const uint32_t bt = bk + dx * (3 * Cfg::BSTAGE >> 4);
+                      tc_mma_f16_ta(d, a_tm, desc(b_lbo | bt), idesc, 1u);                                  // x w_hi
+                      if (SPLIT && part == 0) tc_mma_f16_ta(d, a_tm, desc(b_lbo | (bt + 3 * COUT)), idesc, 1u);  // a_hi x w_lo
                     }
-                    tc_commit(BAR(kTE + tbuf));
-                    if (++tbuf == kTsABufs) { tbuf = 0; tparity ^= 1; }
                   }
                 }
+                tc_commit(BAR(kTE + tgrp));
+                if (++tgrp == kTsGroups) { tgrp = 0; tparity ^= 1; }
               }
               if (!resident) {
                 tc_commit(BAR(kBE + ring_st));
@@ -956,35 +962,44 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
   } else if (warp >= 7) {
-    // ---------------- TMEM loaders: shared-memory plane -> A tile in tensor memory ----------------
+    // ---------------- TMEM loaders: shared-memory plane -> A tiles in tensor memory ----------------
     const int wq = warp & 3;                    // lane quarter this warp may access
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     const uint32_t pos_in_tile = (uint32_t)(30 * wq + lane);  // lane (k, i) <-> position 30 k + i
     const uint32_t plane16 = p.plane_stride >> 4;
     const uint4* sA16 = reinterpret_cast<const uint4*>(sA);
     uint32_t slot = 0, sparity = 0;
-    uint32_t tbuf = 0, tparity = 1;  // parity of the previous release (none during the first round)
-    uint32_t tcount = 0;
+    uint32_t tgrp = 0, tparity = 1;  // parity of the previous release (none during the first round)
+    uint32_t gcount = 0;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int z0 = item_of(item).z0, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
       for (int q = qlo; q <= qhi; ++q) {
         mbar_wait(BAR(slot), sparity);  // TMA has landed this z-plane
         const uint4* plane = sA16 + (size_t)slot * (p.slot_stride >> 4);
         for (int dy = 0; dy < 3; ++dy) {
-          for (int kstep = 0; kstep < KSTEPS; ++kstep) {
-            for (int part = 0; part < P; ++part) {
-              const uint4* src = plane + (size_t)((kstep * 2) * P + part) * plane16 + dy * p.pitch + pos_in_tile;
-              for (int g = 0; g < p.G; ++g, ++tcount) {
-                if (tcount >= kTsABufs) mbar_wait(BAR(kTE + tbuf), tparity);
-                tc_fence_after();
-                const uint4 c0 = src[g * 120], c1 = src[(size_t)P * plane16 + g * 120];
-                tc_st8(tmem_base + lane_base + kTsACol0 + tbuf * 8, c0, c1);
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(BAR(kTF + tbuf));
-                if (++tbuf == kTsABufs) { tbuf = 0; tparity ^= 1; }
+          for (int kstep = 0; kstep < KSTEPS; ++kstep, ++gcount) {
+            // one group = the P * G A tiles of this (plane, dy, K step): loads first, then the TMEM stores, one hand-off
+            uint4 c0[kTsMaxTiles], c1[kTsMaxTiles];
+            const uint4* src = plane + (size_t)(kstep * 2) * P * plane16 + dy * p.pitch + pos_in_tile;
+#pragma unroll
+            for (int i = 0; i < kTsMaxTiles; ++i) {
+              const int part = i / p.G, g = i - part * p.G;  // i = part * G + g
+              if (i < P * p.G) {
+                const uint4* sp = src + (size_t)part * plane16 + g * 120;
+                c0[i] = sp[0];
+                c1[i] = sp[(size_t)P * plane16];
               }
             }
+            if (gcount >= kTsGroups) mbar_wait(BAR(kTE + tgrp), tparity);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + lane_base + kTsACol0 + tgrp * (kTsMaxTiles * 8);
+#pragma unroll
+            for (int i = 0; i < kTsMaxTiles; ++i)
+              if (i < P * p.G) tc_st8(t0 + i * 8, c0[i], c1[i]);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(BAR(kTF + tgrp));
+            if (++tgrp == kTsGroups) { tgrp = 0; tparity ^= 1; }
           }
         }
         if (++slot == kRing) { slot = 0; sparity ^= 1; }
@@ -1020,23 +1035,15 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const bool valid = lane < 30 && row < ty_valid && col < xt_valid;
         for (int pz = z0; pz < z1; ++pz) {
           const size_t vox = ((size_t)pz * p.Y + (y0 + row)) * p.X + (x0 + col);
-          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTsAccCols + (g * T + (pz - z0)) * NB);
+          const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTsAccCols + (g * T + (pz - z0)) * COUT);
 #pragma unroll
           for (int cb = 0; cb < COUT / 16; ++cb) {
             uint32_t r[16];
             tc_ld16(taddr + cb * 16, r);
             float v[16];
-            if (SPLIT) {
-              uint32_t r2[16];
-              tc_ld16(taddr + COUT + cb * 16, r2);
-              tc_wait_ld();
+            tc_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
-            } else {
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-            }
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               v[i] += __ldg(p.bias + cb * 16 + i);
@@ -1050,7 +1057,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           {
             const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-            for (int c = 0; c < NB; c += 16) tc_st16(taddr + c, zero);
+            for (int c = 0; c < COUT; c += 16) tc_st16(taddr + c, zero);
           }
         }
       }
@@ -1541,16 +1548,16 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
     }
   }
   // z-stacked + TMEM-shift variants: M tiles of 120 positions, accumulators G * T * NB <= 224 columns per buffer
-  if (3 * Cfg::NB <= 256 && !getenv("CFB_NO_TSHIFT") && !getenv("CFB_NO_ZSTACK")) {
+  if (!getenv("CFB_NO_TSHIFT") && !getenv("CFB_NO_ZSTACK")) {
     for (auto& e : xts) {
       const int XT = e.first, pitch = XT + 2;
-      for (int T : {2, 3, 4, 6}) {
+      for (int T : {2, 3, 4, 6, 8}) {
         if (T > sz.z && T != 2) continue;
         for (int tyc = ty_cap; tyc >= 2; tyc -= 2) {
           const size_t plane = (size_t)(tyc + 2) * pitch * 16;
           const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
           const int G = ceil_div(tyc * pitch, 120);
-          if (G * T * Cfg::NB > kTsAccCols || slot >= (1u << 18)) continue;
+          if (G * T * COUT > kTsAccCols || Cfg::P * G > kTsMaxTiles || slot >= (1u << 18)) continue;
           const size_t fixed = (size_t)kTsBarBytes + kTailPad + 128;
           if ((size_t)kRing * slot + fixed >= (size_t)kMaxSmem) continue;
           const size_t room = (size_t)kMaxSmem - (size_t)kRing * slot - fixed;
@@ -1629,10 +1636,13 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
       throw std::runtime_error("the fused head+blend tail needs a 16->16 layer");
     }
   }
+  if (t.shift) {
+    run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false>, kThreadsTS);
+    return;
+  }
   if (t.T) {
     if constexpr (3 * Cfg::NB <= 256) {
-      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false>, kThreadsTS);
-      else run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, false>);
+      run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, false>);
       return;
     } else {
       throw std::runtime_error("z-stacked kernel needs 3 * NB <= 256");
@@ -1669,7 +1679,17 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       CFB_CUDA(cudaEventCreate(&e0));
       CFB_CUDA(cudaEventCreate(&e1));
       float best_ms = 1e30f;
-      const size_t n = std::min<size_t>(cands.size(), 40);
+      // the 14 most promising tilings of each kernel variant (per-tap, z-stacked, z-stacked + TMEM shift)
+      std::vector<ConvTile> pick;
+      for (int cls = 0; cls < 3; ++cls) {
+        int taken = 0;
+        for (const ConvTile& c : cands) {
+          const int k = c.shift ? 2 : (c.T ? 1 : 0);
+          if (k == cls && taken < 14) { pick.push_back(c); ++taken; }
+        }
+      }
+      cands.swap(pick);
+      const size_t n = cands.size();
       for (size_t i = 0; i < n; ++i) {
         launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
         CFB_CUDA(cudaEventRecord(e0, s));
@@ -1795,14 +1815,24 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
             }
   CFB_CUDA(cudaMalloc(&out.w_zs, zs.size() * sizeof(__half)));
   CFB_CUDA(cudaMemcpy(out.w_zs, zs.data(), zs.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  // TMEM-shift kernel: the same blocks ordered (dy, kg, dx)
+  // TMEM-shift kernel: blocks ordered (dy, kg, dx); rows of a block = [hi: dz 2,1,0 | lo: dz 2,1,0] x cout
   std::vector<__half> ts(zs.size());
   for (int dy = 0; dy < 3; ++dy)
     for (int g = 0; g < KG; ++g)
       for (int dx = 0; dx < 3; ++dx)
-        std::copy(zs.begin() + ((size_t)(dy * 3 + dx) * KG + g) * (3 * block),
-                  zs.begin() + ((size_t)(dy * 3 + dx) * KG + g + 1) * (3 * block),
-                  ts.begin() + (((size_t)dy * KG + g) * 3 + dx) * (3 * block));
+        for (int kc = 0; kc < KB / 8; ++kc)
+          for (int part = 0; part < parts; ++part)
+            for (int zi = 0; zi < 3; ++zi)
+              for (int co = 0; co < cout; ++co)
+                for (int e = 0; e < 8; ++e) {
+                  const int t = (2 - zi) * 9 + dy * 3 + dx;
+                  const int ci = g * KB + kc * 8 + e;
+                  const float wv = h_w[((size_t)co * cin + ci) * 27 + t];
+                  const __half hi = __float2half_rn(wv);
+                  const size_t row = (size_t)part * 3 * cout + (size_t)zi * cout + co;
+                  ts[(((size_t)dy * KG + g) * 3 + dx) * (3 * block) + ((size_t)kc * 3 * NB + row) * 8 + e] =
+                      part == 0 ? hi : __float2half_rn(wv - __half2float(hi));
+                }
   CFB_CUDA(cudaMalloc(&out.w_ts, ts.size() * sizeof(__half)));
   CFB_CUDA(cudaMemcpy(out.w_ts, ts.data(), ts.size() * sizeof(__half), cudaMemcpyHostToDevice));
 }

@@ -60,10 +60,13 @@ def load() -> C.CDLL:
         return _lib
     from .build import build_native, LIB_PATH
     path = LIB_PATH
+    override = os.environ.get("CFB_NATIVE_LIB")  # development: an instrumented build (python -m chunkflow_b200.build --variant)
     try:
-        path = build_native()
+        path = override if override else build_native()
+        if override and not os.path.exists(override):
+            raise RuntimeError(f"CFB_NATIVE_LIB={override} does not exist")
     except Exception as exc:  # no nvcc on this box: use the prebuilt .so that travelled with the tree
-        if not os.path.exists(LIB_PATH):
+        if override or not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "chunkflow_b200: the CUDA extension libchunkflow_b200.so is missing and could not be built "
                 f"({exc}); there is no CPU fallback") from exc

@@ -33,6 +33,18 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name: str, defines) -> str:
+    """Development build with extra -D flags into _native/libchunkflow_b200_<name>.so (load it with CFB_NATIVE_LIB)."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    out = os.path.join(OUT_DIR, f"libchunkflow_b200_{name}.so")
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, *defines, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *sources(), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
@@ -40,7 +52,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libchunkflow_b200.so")
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *sources(), "-o", LIB_PATH]
+    extra = os.environ.get("CFB_NVCC_DEFINES", "").split()  # development builds only, e.g. -DCFB_TS_TRACE
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC, *sources(), "-o", LIB_PATH]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -53,4 +66,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
+    if "--variant" in sys.argv:  # python -m chunkflow_b200.build --variant trace -DCFB_TS_TRACE
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+        sys.exit(0)
     print(build_native(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -66,6 +66,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Wait of a role that is far off the critical path (epilogue, producers): back off between polls so that the spinning
+// warp does not take issue slots from the MMA-issuing warp on the same scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+#ifdef CFB_TS_RELAX
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 // One elected lane of a converged warp (PTX elect.sync).  ptxas knows the guarded region is
 // single-threaded and keeps descriptors in uniform registers; a `lane == 0` test instead makes
 // it wrap every tcgen05.mma in an ELECT/branch loop.
@@ -230,6 +244,24 @@ __device__ __forceinline__ void head_blend_16(const float (&v)[16], const FusedT
   }
 }
 
+#ifdef CFB_TS_TRACE
+bool g_trace_print = false;   // set around the post-tuning launch
+int g_trace_left = 64;        // print at most this many launches
+#endif
+// Development instrumentation of the TMEM-shift kernel (build with CFB_NVCC_DEFINES=-DCFB_TS_TRACE): ablation switches
+// (-DCFB_TS_ABLATE + env CFB_ABLATE, results become wrong) and per-role mbarrier wait-cycle counters.  Compiled out of the product build:
+// the single MMA-issuing thread is issue bound and even a predicate test per MMA costs ~20 %.
+#ifdef CFB_TS_ABLATE
+#define CFB_ABL(p, bit) (((p).ablate & (bit)) != 0)
+#else
+#define CFB_ABL(p, bit) false
+#endif
+#ifdef CFB_TS_TRACE
+#define CFB_TRACE_WAIT(ctr, stmt) do { const long long t_ = clock64(); stmt; (ctr) += clock64() - t_; } while (0)
+#else
+#define CFB_TRACE_WAIT(ctr, stmt) do { stmt; } while (0)
+#endif
+
 struct UmmaConvParams {
   int Z, Y, X;
   int XT, TY, pitch, tile_stride, G;
@@ -249,6 +281,9 @@ struct UmmaConvParams {
   FusedTail tail;  // used by the TAIL = true instantiations only
   int total_items; // z-stacked kernel: work items = batch x tiles x z blocks (persistent CTAs)
   const __half* wpacked_ts;  // TMEM-shift kernel: (dy, kg) triples of z-stacked blocks
+  int ablate;      // CFB_TS_TRACE builds only: 1 no global stores, 2 no epilogue TMEM reads, 4 no loader copies,
+                   // 8 no shifts, 16 no MMAs, 32 no TMA plane loads
+  long long* trace;  // CFB_TS_TRACE builds only: 16 cycle counters per CTA
 };
 
 constexpr int kRing = 3;       // z-plane ring slots
@@ -841,6 +876,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ---------------- A producer (TMA z-plane ring), as in the z-stacked kernel ----------------
     if (elect_one()) {
       const uint32_t tx_bytes = (uint32_t)Cfg::NPL * p.plane_stride;
+      [[maybe_unused]] long long tr_wait0 = 0, tr_t0 = clock64();
       int slot = 0, ld = 0;
       uint32_t prev_parity = 1;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -849,7 +885,10 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int plane_a0 = it.b * p.planes_a * P, plane_b0 = it.b * p.planes_b * P;
         const int qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
         for (int q = qlo; q <= qhi; ++q, ++ld) {
-          if (ld >= kRing) mbar_wait(BAR(3 + slot), prev_parity);
+          if (ld >= kRing) CFB_TRACE_WAIT(tr_wait0, mbar_wait_relaxed(BAR(3 + slot), prev_parity));
+          if (CFB_ABL(p, 32)) {
+            mbar_arrive(BAR(slot));
+          } else {
           mbar_expect_tx(BAR(slot), tx_bytes);
           const uint32_t dst = smem_u32(sA + (size_t)slot * p.slot_stride);
           const uint32_t dst_b = dst + (uint32_t)(p.planes_a * P) * p.plane_stride;
@@ -860,9 +899,13 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             tma_load_4d(dst, &mapA, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_a0);
             if (p.planes_b > 0) tma_load_4d(dst_b, &mapB, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_b0);
           }
+          }
           if (++slot == kRing) { slot = 0; prev_parity ^= 1; }
         }
       }
+#ifdef CFB_TS_TRACE
+      if (p.trace) { p.trace[blockIdx.x * 16 + 9] = clock64() - tr_t0; p.trace[blockIdx.x * 16 + 10] = tr_wait0; }
+#endif
     }
   } else if (warp == 1) {
     // ---------------- B producer: 3 * KG (dy, kg) triples per input plane ----------------
@@ -877,7 +920,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t total = p.bresident ? per_plane : planes * per_plane;
       uint32_t st = 0, blk = 0, prev_parity = 1;
       for (uint32_t i = 0; i < total; ++i) {
-        if (i >= nbs) mbar_wait(BAR(kBE + st), prev_parity);
+        if (i >= nbs) mbar_wait_relaxed(BAR(kBE + st), prev_parity);
         mbar_expect_tx(BAR(kBF + st), BSTAGE);
         for (int part = 0; part < 9; ++part)  // bulk copies of at most one per-tap block each
           bulk_load(smem_u32(sB + st * BSTAGE + part * Cfg::BSTAGE),
@@ -901,10 +944,11 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       uint32_t slot = 0;
       uint32_t tgrp = 0, tparity = 0;  // TMEM A-tile group ring position
       bool first_plane = true;
+      [[maybe_unused]] long long tr_acc = 0, tr_tf = 0, tr_b = 0, tr_issue = 0, tr_t0 = clock64();
       int jj = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
         const uint32_t buf = (uint32_t)jj & 1u;
-        mbar_wait(BAR(kAccE + buf), (uint32_t)(jj >> 1) & 1u);
+        CFB_TRACE_WAIT(tr_acc, mbar_wait(BAR(kAccE + buf), (uint32_t)(jj >> 1) & 1u));
         tc_fence_after();
         const int z0 = item_of(item).z0, z1 = min(z0 + T, Z), qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
         const uint32_t dbuf = tmem_base + buf * kTsAccCols;
@@ -912,39 +956,50 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           const int plo = max(q - 1, z0), phi = min(q + 1, z1 - 1);
           const uint32_t ng = (uint32_t)(phi - plo + 1);
           const uint32_t row0 = (uint32_t)(2 - (q - plo + 1)) * COUT;  // first dz row group inside the hi (or lo) rows
+#ifdef CFB_TS_SMALLN
+          const uint32_t idesc = make_idesc(16);  // experiment: quarter-size MMAs (wrong results) to tell issue-bound from tensor-bound
+#else
           const uint32_t idesc = make_idesc((int)(ng * COUT));
+#endif
           const uint32_t dcol0 = dbuf + (uint32_t)(plo - z0) * COUT;
           uint32_t blk = 0;
           for (int dy = 0; dy < 3; ++dy) {
             for (int kg = 0; kg < Cfg::KG; ++kg) {
               uint32_t b16;
               if (resident) {
-                if (first_plane) { mbar_wait(BAR(kBF + blk), 0); tc_fence_after(); }
+                if (first_plane) { CFB_TRACE_WAIT(tr_b, mbar_wait(BAR(kBF + blk), 0)); tc_fence_after(); }
                 b16 = sB16 + blk * (BSTAGE >> 4);
                 ++blk;
               } else {
-                mbar_wait(BAR(kBF + ring_st), ring_parity);
+                CFB_TRACE_WAIT(tr_b, mbar_wait(BAR(kBF + ring_st), ring_parity));
                 tc_fence_after();
                 b16 = sB16 + ring_st * (BSTAGE >> 4);
               }
 #pragma unroll
               for (int ks = 0; ks < Cfg::KS; ++ks) {
                 const uint32_t bk = b16 + (uint32_t)ks * 2u * (3 * NB) + row0;
-                mbar_wait(BAR(kTF + tgrp), tparity);  // the loader warps filled this group of TMEM A tiles
+                CFB_TRACE_WAIT(tr_tf, mbar_wait(BAR(kTF + tgrp), tparity));  // the loader warps filled this group of TMEM A tiles
                 tc_fence_after();
                 uint32_t a_tm = tmem_base + kTsACol0 + tgrp * (kTsMaxTiles * 8);
+#ifdef CFB_TS_TRACE
+                const long long tr_i0 = clock64();
+#endif
                 for (int part = 0; part < P; ++part) {  // A tile part: 0 = hi, 1 = lo
                   uint32_t d = dcol0;
                   for (uint32_t g = 0; g < G; ++g, d += (uint32_t)T * COUT, a_tm += 8) {
 #pragma unroll
                     for (uint32_t dx = 0; dx < 3; ++dx) {
-                      if (dx) tc_shift_down(a_tm);
+                      if (dx && !CFB_ABL(p, 8)) tc_shift_down(a_tm);
                       const uint32_t bt = bk + dx * (3 * Cfg::BSTAGE >> 4);
+                      if (CFB_ABL(p, 16)) continue;
                       tc_mma_f16_ta(d, a_tm, desc(b_lbo | bt), idesc, 1u);                                  // x w_hi
                       if (SPLIT && part == 0) tc_mma_f16_ta(d, a_tm, desc(b_lbo | (bt + 3 * COUT)), idesc, 1u);  // a_hi x w_lo
                     }
                   }
                 }
+#ifdef CFB_TS_TRACE
+                tr_issue += clock64() - tr_i0;
+#endif
                 tc_commit(BAR(kTE + tgrp));
                 if (++tgrp == kTsGroups) { tgrp = 0; tparity ^= 1; }
               }
@@ -960,6 +1015,12 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         tc_commit(BAR(kAccF + buf));
       }
+#ifdef CFB_TS_TRACE
+      if (p.trace) {
+        long long* t = p.trace + blockIdx.x * 16;
+        t[0] = clock64() - tr_t0; t[1] = tr_acc; t[2] = tr_tf; t[3] = tr_b; t[11] = tr_issue;
+      }
+#endif
     }
   } else if (warp >= 7) {
     // ---------------- TMEM loaders: shared-memory plane -> A tiles in tensor memory ----------------
@@ -971,10 +1032,11 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     uint32_t slot = 0, sparity = 0;
     uint32_t tgrp = 0, tparity = 1;  // parity of the previous release (none during the first round)
     uint32_t gcount = 0;
+    [[maybe_unused]] long long tr_slot = 0, tr_te = 0, tr_t0 = clock64();
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int z0 = item_of(item).z0, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
       for (int q = qlo; q <= qhi; ++q) {
-        mbar_wait(BAR(slot), sparity);  // TMA has landed this z-plane
+        CFB_TRACE_WAIT(tr_slot, mbar_wait(BAR(slot), sparity));  // TMA has landed this z-plane
         const uint4* plane = sA16 + (size_t)slot * (p.slot_stride >> 4);
         for (int dy = 0; dy < 3; ++dy) {
           for (int kstep = 0; kstep < KSTEPS; ++kstep, ++gcount) {
@@ -984,18 +1046,18 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
             for (int i = 0; i < kTsMaxTiles; ++i) {
               const int part = i / p.G, g = i - part * p.G;  // i = part * G + g
-              if (i < P * p.G) {
+              if (i < P * p.G && !CFB_ABL(p, 4)) {
                 const uint4* sp = src + (size_t)part * plane16 + g * 120;
                 c0[i] = sp[0];
                 c1[i] = sp[(size_t)P * plane16];
               }
             }
-            if (gcount >= kTsGroups) mbar_wait(BAR(kTE + tgrp), tparity);
+            if (gcount >= kTsGroups) CFB_TRACE_WAIT(tr_te, mbar_wait(BAR(kTE + tgrp), tparity));
             tc_fence_after();
             const uint32_t t0 = tmem_base + lane_base + kTsACol0 + tgrp * (kTsMaxTiles * 8);
 #pragma unroll
             for (int i = 0; i < kTsMaxTiles; ++i)
-              if (i < P * p.G) tc_st8(t0 + i * 8, c0[i], c1[i]);
+              if (i < P * p.G && !CFB_ABL(p, 4)) tc_st8(t0 + i * 8, c0[i], c1[i]);
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(BAR(kTF + tgrp));
@@ -1005,6 +1067,12 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (++slot == kRing) { slot = 0; sparity ^= 1; }
       }
     }
+#ifdef CFB_TS_TRACE
+    if (p.trace && warp == 7 && lane == 0) {
+      long long* t = p.trace + blockIdx.x * 16;
+      t[4] = clock64() - tr_t0; t[5] = tr_slot; t[6] = tr_te;
+    }
+#endif
   } else {
     // ---------------- epilogue (warps 3..6) ----------------
     const int wq = warp & 3;
@@ -1021,13 +1089,14 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const float inv_pitch = 1.0f / (float)p.pitch;
     uint4* out16 = reinterpret_cast<uint4*>(p.out);
     int jj = 0;
+    [[maybe_unused]] long long tr_accf = 0, tr_t0 = clock64();
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++jj) {
       const int buf = jj & 1;
       const Item it = item_of(item);
       const int b = it.b, x0 = it.x0, y0 = it.y0, z0 = it.z0, z1 = min(z0 + T, Z);
       const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
       if constexpr (TAIL) pp = p.tail.patches[b];
-      mbar_wait(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u);
+      CFB_TRACE_WAIT(tr_accf, mbar_wait_relaxed(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u));
       tc_fence_after();
       for (int g = 0; g < p.G; ++g) {
         const int qpos = g * 120 + 30 * wq + lane;
@@ -1039,7 +1108,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
           for (int cb = 0; cb < COUT / 16; ++cb) {
             uint32_t r[16];
-            tc_ld16(taddr + cb * 16, r);
+            if (!CFB_ABL(p, 2)) tc_ld16(taddr + cb * 16, r);
             float v[16];
             tc_wait_ld();
 #pragma unroll
@@ -1049,7 +1118,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               v[i] += __ldg(p.bias + cb * 16 + i);
               if (p.relu) v[i] = fmaxf(v[i], 0.f);
             }
-            if (valid) {
+            if (valid && !CFB_ABL(p, 1)) {
               if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, pz, y0 + row, x0 + col);
               else store_cp8_16<COUT, SPLIT>(v, cb, b, vox, plane_vox, out16);
             }
@@ -1065,6 +1134,12 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       tc_fence_before();
       mbar_arrive(BAR(kAccE + buf));
     }
+#ifdef CFB_TS_TRACE
+    if (p.trace && warp == 3 && lane == 0) {
+      long long* t = p.trace + blockIdx.x * 16;
+      t[7] = clock64() - tr_t0; t[8] = tr_accf;
+    }
+#endif
   }
 
   tc_fence_before();
@@ -1540,8 +1615,9 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
           const double lookahead = t.resident ? 1e9 : (double)(bs - 1) * G * Cfg::KS * Cfg::P * 3;
           const double quant = 1.0;  // persistent CTAs over (column, z block) items: no wave quantisation
           // one tile read serves three z-taps: (T + 2) / (3 T) of the plain kernel's operand traffic
+          const double wbytes = t.resident ? 0.0 : 27.0 * Cfg::KG * Cfg::BSTAGE * (double)(T + 2) / ((double)T * useful);
           t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T) + 0.25)) * quant +
-                   (lookahead >= 96 ? 0.0 : 0.4 * (96 - lookahead) / 96);
+                   (lookahead >= 96 ? 0.0 : 0.4 * (96 - lookahead) / 96) + 0.3 * wbytes / 1024.0;
           out.push_back(t);
         }
       }
@@ -1570,7 +1646,10 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
           t.T = T; t.shift = true; t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
           const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
           // tensor/B-bound rather than tile-read bound: about half the z-stacked kernel's cost per position
-          t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T)) * 0.6);
+          // streamed weights are re-fetched from L2 for every (input plane, tile group): bytes per useful output
+          const double wbytes = t.resident ? 0.0 : 27.0 * Cfg::KG * Cfg::BSTAGE * (double)(T + 2) / ((double)T * useful);
+          t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T)) * 0.6) +
+                   0.3 * wbytes / 1024.0;
           out.push_back(t);
         }
       }
@@ -1611,6 +1690,17 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   p.planes_a = ca / 8; p.planes_b = cb / 8;
   p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.wpacked_ts = w.w_ts; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
   p.T = t.T;
+  {
+#ifdef CFB_TS_ABLATE
+    static const int ablate = [] { const char* e = std::getenv("CFB_ABLATE"); return e ? atoi(e) : 0; }();
+    p.ablate = ablate;
+#endif
+#ifdef CFB_TS_TRACE
+    static long long* trace = [] { long long* t = nullptr; cudaMalloc(&t, 256 * 16 * sizeof(long long)); return t; }();
+    p.trace = g_trace_print ? trace : nullptr;
+    if (p.trace) cudaMemsetAsync(trace, 0, 256 * 16 * sizeof(long long), s);
+#endif
+  }
   const size_t bstage = t.shift ? 9 * (size_t)Cfg::BSTAGE : (t.T ? 3 * (size_t)Cfg::BSTAGE : (size_t)Cfg::BSTAGE);
   const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + (t.shift ? kTsBarBytes : kBarBytes) + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
@@ -1624,6 +1714,20 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
     CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, s>>>(mapA, mapB, p);
     CFB_LAUNCH_CHECK();
+#ifdef CFB_TS_TRACE
+    if (p.trace && t.shift && g_trace_left > 0) {
+      --g_trace_left;
+      std::vector<long long> h(256 * 16);
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h.data(), p.trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+      double a[16] = {0};
+      for (int c = 0; c < grid; ++c)
+        for (int i = 0; i < 16; ++i) a[i] += (double)h[c * 16 + i] / grid;
+      fprintf(stderr, "[cfb-trace] %d->%d %dx%dx%d nb=%d T=%d XT=%d TY=%d G=%d items/cta=%.1f | mma: total %.0f wait accE %.0f TF %.0f B %.0f issue %.0f | loader: total %.0f "
+              "wait plane %.0f TE %.0f | epi: total %.0f wait accF %.0f | prodA: total %.0f wait empty %.0f  (cycles, CTA average)\n",
+              CIN, COUT, sz.z, sz.y, sz.x, nb, t.T, t.XT, t.TY, p.G, (double)p.total_items / grid, a[0], a[1], a[2], a[3], a[11], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+    }
+#endif
   };
   if (tail) {
     if constexpr (CIN == 16 && COUT == 16) {
@@ -1685,7 +1789,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
         int taken = 0;
         for (const ConvTile& c : cands) {
           const int k = c.shift ? 2 : (c.T ? 1 : 0);
-          if (k == cls && taken < 14) { pick.push_back(c); ++taken; }
+          if (k == cls && taken < 18) { pick.push_back(c); ++taken; }
         }
       }
       cands.swap(pick);
@@ -1710,7 +1814,13 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
               (int)best.resident, tune ? "tuned ms" : "model cost", best.cost);
     it = w.tuned->emplace(key, best).first;
   }
+#ifdef CFB_TS_TRACE
+  g_trace_print = getenv("CFB_TS_TRACE_PRINT") != nullptr;
+#endif
   launch_tile<CIN, COUT, SPLIT>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
+#ifdef CFB_TS_TRACE
+  g_trace_print = false;
+#endif
 }
 
 

@@ -66,20 +66,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// Wait of a role that is far off the critical path (epilogue, producers): back off between polls so that the spinning
-// warp does not take issue slots from the MMA-issuing warp on the same scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
-#ifdef CFB_TS_RELAX
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(100);
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-#else
-  mbar_wait(bar, parity);
-#endif
-}
 // One elected lane of a converged warp (PTX elect.sync).  ptxas knows the guarded region is
 // single-threaded and keeps descriptors in uniform registers; a `lane == 0` test instead makes
 // it wrap every tcgen05.mma in an ELECT/branch loop.
@@ -281,7 +267,8 @@ struct UmmaConvParams {
   FusedTail tail;  // used by the TAIL = true instantiations only
   int total_items; // z-stacked kernel: work items = batch x tiles x z blocks (persistent CTAs)
   const __half* wpacked_ts;  // TMEM-shift kernel: (dy, kg) triples of z-stacked blocks
-  int ablate;      // CFB_TS_TRACE builds only: 1 no global stores, 2 no epilogue TMEM reads, 4 no loader copies,
+  int niss;        // TMEM-shift kernel: MMA-issuing threads (1 or 2; M tiles are dealt round-robin so every accumulator has ONE issuer)
+  int ablate;      // CFB_TS_ABLATE builds only: 1 no global stores, 2 no epilogue TMEM reads, 4 no loader copies,
                    // 8 no shifts, 16 no MMAs, 32 no TMA plane loads
   long long* trace;  // CFB_TS_TRACE builds only: 16 cycle counters per CTA
 };
@@ -808,7 +795,7 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 // lane (k, i) <-> position 120 g + 30 k + i, i < 30 valid.
 // Weight blocks: (dy, kg) triples of the z-stacked blocks of dx = 0, 1, 2.
 // ------------------------------------------------------------------------------------------
-constexpr int kThreadsTS = 352;   // 11 warps: A producer, B producer, MMA, 4 epilogue, 4 TMEM loaders
+constexpr int kThreadsTS = 384;   // 12 warps: A producer, B producer, MMA issuer 0, 4 epilogue, 4 TMEM loaders, MMA issuer 1
 constexpr int kTsGroups = 2;      // ring of A-tile GROUPS in TMEM; a group = all (part, tile) A tiles of one (plane, dy, K step)
 constexpr int kTsMaxTiles = 8;    // P * G <= 8 tiles of 8 columns per group
 constexpr int kTsACol0 = 384;     // groups live at columns [384, 512)
@@ -855,10 +842,10 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-    for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), 1); mbar_init(BAR(kAccE + i), 128); }
-    for (int i = 0; i < kTsGroups; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); }  // plane slots are released by the 4 loader warps
+    for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), p.niss); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), p.niss); mbar_init(BAR(kAccE + i), 128); }
+    for (int i = 0; i < kTsGroups; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), p.niss); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -885,7 +872,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int plane_a0 = it.b * p.planes_a * P, plane_b0 = it.b * p.planes_b * P;
         const int qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
         for (int q = qlo; q <= qhi; ++q, ++ld) {
-          if (ld >= kRing) CFB_TRACE_WAIT(tr_wait0, mbar_wait_relaxed(BAR(3 + slot), prev_parity));
+          if (ld >= kRing) CFB_TRACE_WAIT(tr_wait0, mbar_wait(BAR(3 + slot), prev_parity));
           if (CFB_ABL(p, 32)) {
             mbar_arrive(BAR(slot));
           } else {
@@ -920,7 +907,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t total = p.bresident ? per_plane : planes * per_plane;
       uint32_t st = 0, blk = 0, prev_parity = 1;
       for (uint32_t i = 0; i < total; ++i) {
-        if (i >= nbs) mbar_wait_relaxed(BAR(kBE + st), prev_parity);
+        if (i >= nbs) mbar_wait(BAR(kBE + st), prev_parity);
         mbar_expect_tx(BAR(kBF + st), BSTAGE);
         for (int part = 0; part < 9; ++part)  // bulk copies of at most one per-tap block each
           bulk_load(smem_u32(sB + st * BSTAGE + part * Cfg::BSTAGE),
@@ -930,18 +917,20 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (++blk == per_plane) blk = 0;
       }
     }
-  } else if (warp == 2) {
-    // ---------------- MMA issuer ----------------
-    if (elect_one()) {
+  } else if (warp == 2 || warp == 11) {
+    // ---------------- MMA issuers: issuer i owns the M tiles g = i, i + niss, ... (and their accumulators) ----------------
+    const uint32_t iss = warp == 2 ? 0u : 1u;
+    if (iss < (uint32_t)p.niss && elect_one()) {
+      const uint32_t niss = (uint32_t)p.niss;
       constexpr uint32_t DESC_HI = 8u | (1u << 14);
       constexpr uint32_t b_lbo = (uint32_t)(3 * NB) << 16;
       const uint32_t sB16 = smem_u32(sB) >> 4;
       const uint32_t G = (uint32_t)p.G;
+      const uint32_t dstep1 = (uint32_t)p.T * COUT, dstep = niss * dstep1, astep = niss * 8;
       const bool resident = p.bresident != 0;
       const uint32_t nbs = (uint32_t)p.bstages;
       auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
       uint32_t ring_st = 0, ring_parity = 0;
-      uint32_t slot = 0;
       uint32_t tgrp = 0, tparity = 0;  // TMEM A-tile group ring position
       bool first_plane = true;
       [[maybe_unused]] long long tr_acc = 0, tr_tf = 0, tr_b = 0, tr_issue = 0, tr_t0 = clock64();
@@ -980,13 +969,14 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const uint32_t bk = b16 + (uint32_t)ks * 2u * (3 * NB) + row0;
                 CFB_TRACE_WAIT(tr_tf, mbar_wait(BAR(kTF + tgrp), tparity));  // the loader warps filled this group of TMEM A tiles
                 tc_fence_after();
-                uint32_t a_tm = tmem_base + kTsACol0 + tgrp * (kTsMaxTiles * 8);
+                const uint32_t a_grp = tmem_base + kTsACol0 + tgrp * (kTsMaxTiles * 8) + iss * 8;
 #ifdef CFB_TS_TRACE
                 const long long tr_i0 = clock64();
 #endif
                 for (int part = 0; part < P; ++part) {  // A tile part: 0 = hi, 1 = lo
-                  uint32_t d = dcol0;
-                  for (uint32_t g = 0; g < G; ++g, d += (uint32_t)T * COUT, a_tm += 8) {
+                  uint32_t d = dcol0 + iss * dstep1;
+                  uint32_t a_tm = a_grp + (uint32_t)part * G * 8;
+                  for (uint32_t g = iss; g < G; g += niss, d += dstep, a_tm += astep) {
 #pragma unroll
                     for (uint32_t dx = 0; dx < 3; ++dx) {
                       if (dx && !CFB_ABL(p, 8)) tc_shift_down(a_tm);
@@ -1010,19 +1000,18 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             }
           }
           first_plane = false;
-          tc_commit(BAR(3 + slot));  // every MMA that depended on this shared-memory plane has completed
-          if (++slot == kRing) slot = 0;
         }
         tc_commit(BAR(kAccF + buf));
       }
 #ifdef CFB_TS_TRACE
       if (p.trace) {
-        long long* t = p.trace + blockIdx.x * 16;
-        t[0] = clock64() - tr_t0; t[1] = tr_acc; t[2] = tr_tf; t[3] = tr_b; t[11] = tr_issue;
+        long long* t = p.trace + blockIdx.x * 16 + (iss ? 12 : 0);
+        if (iss) { t[0] = clock64() - tr_t0; t[1] = tr_issue; }
+        else { t[0] = clock64() - tr_t0; t[1] = tr_acc; t[2] = tr_tf; t[3] = tr_b; t[11] = tr_issue; }
       }
 #endif
     }
-  } else if (warp >= 7) {
+  } else if (warp >= 7 && warp <= 10) {
     // ---------------- TMEM loaders: shared-memory plane -> A tiles in tensor memory ----------------
     const int wq = warp & 3;                    // lane quarter this warp may access
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
@@ -1064,6 +1053,10 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             if (++tgrp == kTsGroups) { tgrp = 0; tparity ^= 1; }
           }
         }
+        // the tensor core never reads A from shared memory in this kernel: once this warp's copies of the plane are
+        // in tensor memory (tcgen05.wait::st above) the slot can be refilled by TMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(3 + slot));
         if (++slot == kRing) { slot = 0; sparity ^= 1; }
       }
     }
@@ -1096,7 +1089,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const int b = it.b, x0 = it.x0, y0 = it.y0, z0 = it.z0, z1 = min(z0 + T, Z);
       const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
       if constexpr (TAIL) pp = p.tail.patches[b];
-      CFB_TRACE_WAIT(tr_accf, mbar_wait_relaxed(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u));
+      CFB_TRACE_WAIT(tr_accf, mbar_wait(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u));
       tc_fence_after();
       for (int g = 0; g < p.G; ++g) {
         const int qpos = g * 120 + 30 * wq + lane;
@@ -1691,6 +1684,8 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.wpacked_ts = w.w_ts; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
   p.T = t.T;
   {
+    static const int max_iss = [] { const char* e = std::getenv("CFB_TS_NISS"); return e ? atoi(e) : 2; }();
+    p.niss = (t.shift && p.G >= 2 && max_iss >= 2) ? 2 : 1;
 #ifdef CFB_TS_ABLATE
     static const int ablate = [] { const char* e = std::getenv("CFB_ABLATE"); return e ? atoi(e) : 0; }();
     p.ablate = ablate;
@@ -1723,9 +1718,9 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
       double a[16] = {0};
       for (int c = 0; c < grid; ++c)
         for (int i = 0; i < 16; ++i) a[i] += (double)h[c * 16 + i] / grid;
-      fprintf(stderr, "[cfb-trace] %d->%d %dx%dx%d nb=%d T=%d XT=%d TY=%d G=%d items/cta=%.1f | mma: total %.0f wait accE %.0f TF %.0f B %.0f issue %.0f | loader: total %.0f "
+      fprintf(stderr, "[cfb-trace] %d->%d %dx%dx%d nb=%d T=%d XT=%d TY=%d G=%d items/cta=%.1f | mma: total %.0f wait accE %.0f TF %.0f B %.0f issue %.0f (issuer 1: total %.0f issue %.0f) | loader: total %.0f "
               "wait plane %.0f TE %.0f | epi: total %.0f wait accF %.0f | prodA: total %.0f wait empty %.0f  (cycles, CTA average)\n",
-              CIN, COUT, sz.z, sz.y, sz.x, nb, t.T, t.XT, t.TY, p.G, (double)p.total_items / grid, a[0], a[1], a[2], a[3], a[11], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
+              CIN, COUT, sz.z, sz.y, sz.x, nb, t.T, t.XT, t.TY, p.G, (double)p.total_items / grid, a[0], a[1], a[2], a[3], a[11], a[12], a[13], a[4], a[5], a[6], a[7], a[8], a[9], a[10]);
     }
 #endif
   };

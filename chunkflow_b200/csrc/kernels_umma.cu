@@ -221,6 +221,22 @@ __device__ __forceinline__ void head_blend_16(const float (&v)[16], const FusedT
   const float m = __ldg(t.mask + ((size_t)oz * t.op.y + oy) * t.op.x + ox) * t.scale;
   float* dst = t.out + ((size_t)gz * t.os.y + gy) * t.os.x + gx;
   const size_t out_vol = (size_t)t.os.z * t.os.y * t.os.x;
+  if (t.channels == 3) {
+    // the affinity head: three independent FMA chains; sigmoid with ex2.approx / rcp.approx (~1e-7 of the exact value,
+    // the tolerance of this path is 1e-3) -- the fused tail is bound by this epilogue, not by the tensor core
+    float a0 = s_head[48], a1 = s_head[49], a2 = s_head[50];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      a0 = fmaf(v[k], s_head[k], a0);
+      a1 = fmaf(v[k], s_head[16 + k], a1);
+      a2 = fmaf(v[k], s_head[32 + k], a2);
+    }
+    const float s0 = __fdividef(m, 1.0f + __expf(-a0)), s1 = __fdividef(m, 1.0f + __expf(-a1)), s2 = __fdividef(m, 1.0f + __expf(-a2));
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(s0) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + out_vol), "f"(s1) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + 2 * out_vol), "f"(s2) : "memory");
+    return;
+  }
   for (int co = 0; co < t.channels; ++co) {
     float acc = s_head[t.channels * 16 + co];
 #pragma unroll
@@ -267,7 +283,8 @@ struct UmmaConvParams {
   FusedTail tail;  // used by the TAIL = true instantiations only
   int total_items; // z-stacked kernel: work items = batch x tiles x z blocks (persistent CTAs)
   const __half* wpacked_ts;  // TMEM-shift kernel: (dy, kg) triples of z-stacked blocks
-  int niss;        // TMEM-shift kernel: MMA-issuing threads (1 or 2; M tiles are dealt round-robin so every accumulator has ONE issuer)
+  int niss;        // TMEM-shift kernel: MMA-issuing threads (1..4; M tiles are dealt round-robin so every accumulator has ONE issuer)
+  int ngroups;     // TMEM-shift kernel: depth of the ring of A-tile groups in tensor memory (2..4)
   int ablate;      // CFB_TS_ABLATE builds only: 1 no global stores, 2 no epilogue TMEM reads, 4 no loader copies,
                    // 8 no shifts, 16 no MMAs, 32 no TMA plane loads
   long long* trace;  // CFB_TS_TRACE builds only: 16 cycle counters per CTA
@@ -796,14 +813,16 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 // Weight blocks: (dy, kg) triples of the z-stacked blocks of dx = 0, 1, 2.
 // ------------------------------------------------------------------------------------------
 constexpr int kThreadsTS = 384;   // 12 warps: A producer, B producer, MMA issuer 0, 4 epilogue, 4 TMEM loaders, MMA issuer 1
-constexpr int kTsGroups = 2;      // ring of A-tile GROUPS in TMEM; a group = all (part, tile) A tiles of one (plane, dy, K step)
+constexpr int kThreadsTSTail = 512;  // fused tail: 4 more epilogue warps
+constexpr int kTsGroups = 4;      // at most: ring of A-tile GROUPS in TMEM (16 tiles / (P * G) of them); a group = all (part, tile) A tiles of one (plane, dy, K step)
+constexpr int kTsMaxIssuers = 2;   // measured: 3 or 4 issuers are no faster than 2 (the kernel is no longer issue bound)
 constexpr int kTsMaxTiles = 8;    // P * G <= 8 tiles of 8 columns per group
 constexpr int kTsACol0 = 384;     // groups live at columns [384, 512)
 constexpr int kTsAccCols = 192;   // accumulator columns per buffer (2 buffers)
 constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsGroups) * 8 + 16 + 640;
 
 template <int CIN, int COUT, bool SPLIT, bool TAIL>
-__global__ void __launch_bounds__(kThreadsTS, 1)
+__global__ void __launch_bounds__(kThreadsTSTail, 1)
 conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const UmmaConvParams p) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
@@ -814,6 +833,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // along N here: a_hi x w_hi, a_hi x w_lo and a_lo x w_hi all accumulate into the same COUT columns of a plane
   // (half the TMEM per plane -> twice the z-stacking depth T, fewer tensor cycles and fewer weight bytes per tap).
   constexpr int KSTEPS = CIN / 16;
+  constexpr int kEpiSets = TAIL ? 2 : 1;  // the fused tail is epilogue bound: 8 epilogue warps (launched with 512 threads), else 4 (384)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
 
@@ -837,14 +857,14 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   float* s_head = reinterpret_cast<float*>(bars + kTE + kTsGroups + 2);
   PatchPos pp{};
   if constexpr (TAIL) {
-    for (int i = threadIdx.x; i < p.tail.channels * 16; i += kThreadsTS) s_head[i] = p.tail.head_w[i];
-    for (int i = threadIdx.x; i < p.tail.channels; i += kThreadsTS) s_head[p.tail.channels * 16 + i] = p.tail.head_b[i];
+    for (int i = threadIdx.x; i < p.tail.channels * 16; i += blockDim.x) s_head[i] = p.tail.head_w[i];
+    for (int i = threadIdx.x; i < p.tail.channels; i += blockDim.x) s_head[p.tail.channels * 16 + i] = p.tail.head_b[i];
   }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); }  // plane slots are released by the 4 loader warps
     for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), p.niss); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), p.niss); mbar_init(BAR(kAccE + i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), p.niss); mbar_init(BAR(kAccE + i), 128 * kEpiSets); }
     for (int i = 0; i < kTsGroups; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), p.niss); }
     fence_barrier_init();
     fence_proxy_async();
@@ -919,7 +939,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
   } else if (warp == 2 || warp == 11) {
     // ---------------- MMA issuers: issuer i owns the M tiles g = i, i + niss, ... (and their accumulators) ----------------
-    const uint32_t iss = warp == 2 ? 0u : 1u;
+    const uint32_t iss = warp == 2 ? 0u : (uint32_t)(warp - 10);
     if (iss < (uint32_t)p.niss && elect_one()) {
       const uint32_t niss = (uint32_t)p.niss;
       constexpr uint32_t DESC_HI = 8u | (1u << 14);
@@ -927,6 +947,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint32_t sB16 = smem_u32(sB) >> 4;
       const uint32_t G = (uint32_t)p.G;
       const uint32_t dstep1 = (uint32_t)p.T * COUT, dstep = niss * dstep1, astep = niss * 8;
+      const uint32_t ngroups = (uint32_t)p.ngroups, gstride = (uint32_t)(P * p.G * 8);
       const bool resident = p.bresident != 0;
       const uint32_t nbs = (uint32_t)p.bstages;
       auto desc = [](uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; };
@@ -969,7 +990,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const uint32_t bk = b16 + (uint32_t)ks * 2u * (3 * NB) + row0;
                 CFB_TRACE_WAIT(tr_tf, mbar_wait(BAR(kTF + tgrp), tparity));  // the loader warps filled this group of TMEM A tiles
                 tc_fence_after();
-                const uint32_t a_grp = tmem_base + kTsACol0 + tgrp * (kTsMaxTiles * 8) + iss * 8;
+                const uint32_t a_grp = tmem_base + kTsACol0 + tgrp * gstride + iss * 8;
 #ifdef CFB_TS_TRACE
                 const long long tr_i0 = clock64();
 #endif
@@ -991,7 +1012,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 tr_issue += clock64() - tr_i0;
 #endif
                 tc_commit(BAR(kTE + tgrp));
-                if (++tgrp == kTsGroups) { tgrp = 0; tparity ^= 1; }
+                if (++tgrp == ngroups) { tgrp = 0; tparity ^= 1; }
               }
               if (!resident) {
                 tc_commit(BAR(kBE + ring_st));
@@ -1006,7 +1027,8 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #ifdef CFB_TS_TRACE
       if (p.trace) {
         long long* t = p.trace + blockIdx.x * 16 + (iss ? 12 : 0);
-        if (iss) { t[0] = clock64() - tr_t0; t[1] = tr_issue; }
+        if (iss > 1) {
+        } else if (iss) { t[0] = clock64() - tr_t0; t[1] = tr_issue; }
         else { t[0] = clock64() - tr_t0; t[1] = tr_acc; t[2] = tr_tf; t[3] = tr_b; t[11] = tr_issue; }
       }
 #endif
@@ -1021,6 +1043,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     uint32_t slot = 0, sparity = 0;
     uint32_t tgrp = 0, tparity = 1;  // parity of the previous release (none during the first round)
     uint32_t gcount = 0;
+    const uint32_t ngroups = (uint32_t)p.ngroups, gstride = (uint32_t)(P * p.G * 8);
     [[maybe_unused]] long long tr_slot = 0, tr_te = 0, tr_t0 = clock64();
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int z0 = item_of(item).z0, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
@@ -1041,16 +1064,16 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 c1[i] = sp[(size_t)P * plane16];
               }
             }
-            if (gcount >= kTsGroups) CFB_TRACE_WAIT(tr_te, mbar_wait(BAR(kTE + tgrp), tparity));
+            if (gcount >= ngroups) CFB_TRACE_WAIT(tr_te, mbar_wait(BAR(kTE + tgrp), tparity));
             tc_fence_after();
-            const uint32_t t0 = tmem_base + lane_base + kTsACol0 + tgrp * (kTsMaxTiles * 8);
+            const uint32_t t0 = tmem_base + lane_base + kTsACol0 + tgrp * gstride;
 #pragma unroll
             for (int i = 0; i < kTsMaxTiles; ++i)
               if (i < P * p.G && !CFB_ABL(p, 4)) tc_st8(t0 + i * 8, c0[i], c1[i]);
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(BAR(kTF + tgrp));
-            if (++tgrp == kTsGroups) { tgrp = 0; tparity ^= 1; }
+            if (++tgrp == ngroups) { tgrp = 0; tparity ^= 1; }
           }
         }
         // the tensor core never reads A from shared memory in this kernel: once this warp's copies of the plane are
@@ -1067,12 +1090,14 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
 #endif
   } else {
-    // ---------------- epilogue (warps 3..6) ----------------
+    // ---------------- epilogue (warps 3..6 = set 0, warps 12..15 = set 1): the two warps of a lane quarter take
+    // alternate (tile, plane) steps -- a step is a latency chain (tcgen05.ld, convert, store / head + sigmoid + red) ----------------
     const int wq = warp & 3;
+    const int eset = (kEpiSets == 2 && warp >= 12) ? 1 : 0;
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     {
       const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < 2 * kTsAccCols; c += 16) tc_st16(tmem_base + lane_base + c, zero);
+      for (int c = eset * kTsAccCols; c < (kEpiSets == 2 ? eset + 1 : 2) * kTsAccCols; c += 16) tc_st16(tmem_base + lane_base + c, zero);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(kAccE + 0));
@@ -1096,6 +1121,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int row = __float2int_rd(((float)qpos + 0.5f) * inv_pitch), col = qpos - row * p.pitch;
         const bool valid = lane < 30 && row < ty_valid && col < xt_valid;
         for (int pz = z0; pz < z1; ++pz) {
+          if (kEpiSets == 2 && ((g * T + (pz - z0)) & 1) != eset) continue;
           const size_t vox = ((size_t)pz * p.Y + (y0 + row)) * p.X + (x0 + col);
           const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTsAccCols + (g * T + (pz - z0)) * COUT);
 #pragma unroll
@@ -1684,8 +1710,9 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.wpacked_ts = w.w_ts; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
   p.T = t.T;
   {
-    static const int max_iss = [] { const char* e = std::getenv("CFB_TS_NISS"); return e ? atoi(e) : 2; }();
-    p.niss = (t.shift && p.G >= 2 && max_iss >= 2) ? 2 : 1;
+    static const int max_iss = [] { const char* e = std::getenv("CFB_TS_NISS"); return e ? atoi(e) : kTsMaxIssuers; }();
+    p.niss = t.shift ? std::max(1, std::min<int>(std::min<int>(p.G, max_iss), kTsMaxIssuers)) : 1;
+    p.ngroups = t.shift ? std::max(2, std::min<int>(kTsGroups, 16 / (Cfg::P * p.G))) : 0;
 #ifdef CFB_TS_ABLATE
     static const int ablate = [] { const char* e = std::getenv("CFB_ABLATE"); return e ? atoi(e) : 0; }();
     p.ablate = ablate;
@@ -1727,7 +1754,7 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   if (tail) {
     if constexpr (CIN == 16 && COUT == 16) {
       p.tail = *tail;
-      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, true>, kThreadsTS);
+      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, true>, kThreadsTSTail);
       else if (t.T) run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, true>);
       else run(conv3_umma_kernel<CIN, COUT, SPLIT, true>);
       return;
@@ -1778,13 +1805,16 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       CFB_CUDA(cudaEventCreate(&e0));
       CFB_CUDA(cudaEventCreate(&e1));
       float best_ms = 1e30f;
-      // the 14 most promising tilings of each kernel variant (per-tap, z-stacked, z-stacked + TMEM shift)
+      // the most promising tilings of each kernel variant: per-tap, z-stacked, and z-stacked + TMEM shift with
+      // 1, 2 and >= 3 M tiles per group (= MMA-issuing threads; the static model ranks these poorly against each other)
       std::vector<ConvTile> pick;
-      for (int cls = 0; cls < 3; ++cls) {
+      const int quota[5] = {8, 12, 10, 12, 12};
+      for (int cls = 0; cls < 5; ++cls) {
         int taken = 0;
         for (const ConvTile& c : cands) {
-          const int k = c.shift ? 2 : (c.T ? 1 : 0);
-          if (k == cls && taken < 18) { pick.push_back(c); ++taken; }
+          const int g = ceil_div(c.TY * (c.XT + 2), 120);
+          const int k = c.shift ? (g == 1 ? 2 : (g == 2 ? 3 : 4)) : (c.T ? 1 : 0);
+          if (k == cls && taken < quota[cls]) { pick.push_back(c); ++taken; }
         }
       }
       cands.swap(pick);
@@ -1798,6 +1828,10 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
         float ms = 0.f;
         CFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (ms < best_ms) { best_ms = ms; best = cands[i]; }
+        if (getenv("CFB_DEBUG_TUNE"))
+          fprintf(stderr, "[cfb-tune] %d->%d %dx%dx%d nb=%d: T=%d%s XT=%d TY=%d G=%d bstages=%d resident=%d  %.3f ms\n", CIN, COUT, sz.z, sz.y, sz.x, nb,
+                  cands[i].T, cands[i].shift ? "+shift" : "", cands[i].XT, cands[i].TY, ceil_div(cands[i].TY * (cands[i].XT + 2), cands[i].shift ? 120 : 128),
+                  cands[i].bstages, (int)cands[i].resident, ms);
       }
       cudaEventDestroy(e0);
       cudaEventDestroy(e1);

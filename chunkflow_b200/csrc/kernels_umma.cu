@@ -284,6 +284,7 @@ struct UmmaConvParams {
   int total_items; // z-stacked kernel: work items = batch x tiles x z blocks (persistent CTAs)
   const __half* wpacked_ts;  // TMEM-shift kernel: (dy, kg) triples of z-stacked blocks
   int niss;        // TMEM-shift kernel: MMA-issuing threads (1..4; M tiles are dealt round-robin so every accumulator has ONE issuer)
+  int ring;        // TMEM-shift kernel: z-plane slots in shared memory (2 or 3)
   int ngroups;     // TMEM-shift kernel: depth of the ring of A-tile groups in tensor memory (2..4)
   int ablate;      // CFB_TS_ABLATE builds only: 1 no global stores, 2 no epilogue TMEM reads, 4 no loader copies,
                    // 8 no shifts, 16 no MMAs, 32 no TMA plane loads
@@ -846,8 +847,9 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     return Item{col / ncols, (col % p.tiles_x) * p.XT, ((col / p.tiles_x) % p.tiles_y) * p.TY, j * p.T};
   };
 
+  const int ring = p.ring;  // plane slots (2 or 3)
   uint8_t* sA = smem;
-  uint8_t* sB = smem + kRing * p.slot_stride;
+  uint8_t* sB = smem + ring * p.slot_stride;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.bstages * BSTAGE);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -892,7 +894,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int plane_a0 = it.b * p.planes_a * P, plane_b0 = it.b * p.planes_b * P;
         const int qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
         for (int q = qlo; q <= qhi; ++q, ++ld) {
-          if (ld >= kRing) CFB_TRACE_WAIT(tr_wait0, mbar_wait(BAR(3 + slot), prev_parity));
+          if (ld >= ring) CFB_TRACE_WAIT(tr_wait0, mbar_wait(BAR(3 + slot), prev_parity));
           if (CFB_ABL(p, 32)) {
             mbar_arrive(BAR(slot));
           } else {
@@ -907,7 +909,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             if (p.planes_b > 0) tma_load_4d(dst_b, &mapB, BAR(slot), 2 * (x0 - 1), y0 - 1, q, plane_b0);
           }
           }
-          if (++slot == kRing) { slot = 0; prev_parity ^= 1; }
+          if (++slot == ring) { slot = 0; prev_parity ^= 1; }
         }
       }
 #ifdef CFB_TS_TRACE
@@ -1080,7 +1082,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         // in tensor memory (tcgen05.wait::st above) the slot can be refilled by TMA
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(3 + slot));
-        if (++slot == kRing) { slot = 0; sparity ^= 1; }
+        if (++slot == ring) { slot = 0; sparity ^= 1; }
       }
     }
 #ifdef CFB_TS_TRACE
@@ -1654,22 +1656,28 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
           const int G = ceil_div(tyc * pitch, 120);
           if (G * T * COUT > kTsAccCols || Cfg::P * G > kTsMaxTiles || slot >= (1u << 18)) continue;
           const size_t fixed = (size_t)kTsBarBytes + kTailPad + 128;
-          if ((size_t)kRing * slot + fixed >= (size_t)kMaxSmem) continue;
-          const size_t room = (size_t)kMaxSmem - (size_t)kRing * slot - fixed;
+          for (int ring = 3; ring >= 2; --ring) {
+          // two plane slots are enough in steady state (the loaders free a slot as soon as its copies are in tensor memory)
+          // and leave room for larger tiles / resident weights on the wide layers
+          if (ring == 2 && CIN < 32) continue;
+          if ((size_t)ring * slot + fixed >= (size_t)kMaxSmem) continue;
+          const size_t room = (size_t)kMaxSmem - (size_t)ring * slot - fixed;
           const int all_blocks = 3 * Cfg::KG;
           const int bstage = 9 * Cfg::BSTAGE;
           int bs = (int)std::min<size_t>(room / bstage, kMaxBStages);
           if (bs >= all_blocks) bs = all_blocks;
           if (bs < 2) continue;
           ConvTile t;
+          t.ring = ring;
           t.T = T; t.shift = true; t.XT = XT; t.TY = tyc; t.bstages = bs; t.resident = bs == all_blocks; t.wide = e.second;
           const double useful = (double)std::min(tyc, sz.y) * std::min(XT, sz.x);
           // tensor/B-bound rather than tile-read bound: about half the z-stacked kernel's cost per position
           // streamed weights are re-fetched from L2 for every (input plane, tile group): bytes per useful output
           const double wbytes = t.resident ? 0.0 : 27.0 * Cfg::KG * Cfg::BSTAGE * (double)(T + 2) / ((double)T * useful);
           t.cost = (((double)(tyc + 2) * pitch / useful) * 0.5 + ((double)G * 128 / useful) * ((double)(T + 2) / (3.0 * T)) * 0.6) +
-                   0.3 * wbytes / 1024.0;
+                   0.3 * wbytes / 1024.0 + (ring == 2 ? 0.02 : 0.0);
           out.push_back(t);
+          }
         }
       }
     }
@@ -1724,7 +1732,8 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
 #endif
   }
   const size_t bstage = t.shift ? 9 * (size_t)Cfg::BSTAGE : (t.T ? 3 * (size_t)Cfg::BSTAGE : (size_t)Cfg::BSTAGE);
-  const size_t smem = (size_t)kRing * p.slot_stride + (size_t)p.bstages * bstage + (t.shift ? kTsBarBytes : kBarBytes) + kTailPad + 128;
+  p.ring = t.shift ? t.ring : kRing;
+  const size_t smem = (size_t)p.ring * p.slot_stride + (size_t)p.bstages * bstage + (t.shift ? kTsBarBytes : kBarBytes) + kTailPad + 128;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
   int grid = nb * p.tiles_x * p.tiles_y;
@@ -1829,8 +1838,8 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
         CFB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         if (ms < best_ms) { best_ms = ms; best = cands[i]; }
         if (getenv("CFB_DEBUG_TUNE"))
-          fprintf(stderr, "[cfb-tune] %d->%d %dx%dx%d nb=%d: T=%d%s XT=%d TY=%d G=%d bstages=%d resident=%d  %.3f ms\n", CIN, COUT, sz.z, sz.y, sz.x, nb,
-                  cands[i].T, cands[i].shift ? "+shift" : "", cands[i].XT, cands[i].TY, ceil_div(cands[i].TY * (cands[i].XT + 2), cands[i].shift ? 120 : 128),
+          fprintf(stderr, "[cfb-tune] %d->%d %dx%dx%d nb=%d: T=%d%s%s XT=%d TY=%d G=%d bstages=%d resident=%d  %.3f ms\n", CIN, COUT, sz.z, sz.y, sz.x, nb,
+                  cands[i].T, cands[i].shift ? "+shift" : "", cands[i].ring == 2 ? " ring2" : "", cands[i].XT, cands[i].TY, ceil_div(cands[i].TY * (cands[i].XT + 2), cands[i].shift ? 120 : 128),
                   cands[i].bstages, (int)cands[i].resident, ms);
       }
       cudaEventDestroy(e0);
@@ -1839,7 +1848,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
     }
     if (getenv("CFB_DEBUG_CFG"))
       fprintf(stderr, "[cfb] conv3 %d->%d split=%d size=%dx%dx%d nb=%d: zstack T=%d%s XT=%d%s TY=%d bstages=%d resident=%d (%s %.3f)\n",
-              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.T, best.shift ? "+shift" : "", best.XT, best.wide ? "w" : "", best.TY, best.bstages,
+              CIN, COUT, (int)SPLIT, sz.z, sz.y, sz.x, nb, best.T, best.shift ? (best.ring == 2 ? "+shift(ring2)" : "+shift") : "", best.XT, best.wide ? "w" : "", best.TY, best.bstages,
               (int)best.resident, tune ? "tuned ms" : "model cost", best.cost);
     it = w.tuned->emplace(key, best).first;
   }

@@ -29,6 +29,7 @@ struct ConvTile {
   int T = 0;  // > 0: z-stacked kernel with T output planes per job
   bool shift = false;  // z-stacked + TMEM-resident activation tile with tcgen05.shift for the dx taps
   bool resident = false, wide = false;
+  int ring = 3;  // z-plane ring slots in shared memory (TMEM-shift kernel: 2 or 3)
   double cost = 0.0;
 };
 

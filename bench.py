@@ -238,20 +238,25 @@ def main():
     dom_ms, dom_launches = layers[dom]
     dom_flop_per_launch = CONV3_FLOP[dom] * P * pvox / dom_launches
     achieved = dom_flop_per_launch / (dom_ms / dom_launches / 1e3) / 1e12 if dom_ms > 0 else 0.0
-    traffic = None
+    traffic, pipe_note = None, ""
     try:  # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_traffic.json), scaled to this batch
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["layers"].get(dom)
+        tl = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["layers"]
+        t = tl.get(dom)
         if t and t.get("dram_bytes_per_patch"):
             traffic = t["dram_bytes_per_patch"] * P / dom_launches
+        pipes = [v["tensor_pipe_active_pct"] for k, v in tl.items() if k in CONV3_FLOP and "conv3" in v.get("kernel", "")]
+        if pipes:
+            pipe_note = "; ncu tensor-pipe active %.0f-%.0f %% over the 3x3x3 layers, %.0f %% on this one" % (
+                min(pipes), max(pipes), (t or {}).get("tensor_pipe_active_pct", float("nan")))
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": f"{dom}: tcgen05 3x3x3 convolution (conv3_zs_umma_kernel / conv3_umma_kernel)",
+    roofline = {"bound": "tensor", "kernel": f"{dom}: tcgen05 3x3x3 convolution (conv3_ts_umma_kernel: z-stacked, A operand in tensor memory)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
                 "traffic": traffic, "launches": dom_launches, "ms_per_launch": dom_ms / max(dom_launches, 1),
                 "algorithmic_flop_per_launch": dom_flop_per_launch,
-                "note": "fp16 hi/lo split executes ~2x these algorithmic FLOPs on the tensor pipe; ncu tensor-pipe active 33-56 % "
-                        "(profiles/r01_ncu_full_summary.md)",
+                "note": "the fp16 hi/lo split (f16x3) executes 3x these algorithmic FLOPs on the tensor pipe" + pipe_note +
+                        " (profiles/r01_ncu_full_summary.md)",
                 "conv_stack": {"achieved": conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0, "unit": "TFLOP/s",
                                "ms_per_chunk": conv_ms, "launches": conv_launches, "algorithmic_flop_per_chunk": conv_flop}}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)

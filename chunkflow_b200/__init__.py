@@ -14,4 +14,7 @@ def __getattr__(name):
     if name == "Inferencer":
         from .flow.divid_conquer.inferencer import Inferencer
         return Inferencer
+    if name == "DeviceChunk":
+        from .chunk.device import DeviceChunk
+        return DeviceChunk
     raise AttributeError(name)

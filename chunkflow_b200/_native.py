@@ -17,6 +17,7 @@ ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED =
 FRAMEWORK_UNET3L, FRAMEWORK_IDENTITY = 0, 1
 PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA = 0, 1, 2
 DTYPE_U8, DTYPE_F32 = 0, 1
+QUANTIZE_XY, QUANTIZE_Z = 0, 1
 
 # every symbol include/chunkflow_b200.h declares
 EXPORTS = (
@@ -25,6 +26,7 @@ EXPORTS = (
     "cfb_infer_chunk_device", "cfb_infer_chunk_host", "cfb_infer_slab_device", "cfb_normalize_device",
     "cfb_patch_forward_host", "cfb_make_patch_mask", "cfb_plugin_begin", "cfb_plugin_extract", "cfb_plugin_blend",
     "cfb_plugin_end", "cfb_last_timing", "cfb_set_profiling", "cfb_layer_timing", "cfb_debug_net_forward_host", "cfb_debug_conv3_host",
+    "cfb_normalize_contrast_device", "cfb_maskout_device", "cfb_crop_margin_device", "cfb_quantize_device",
 )
 
 
@@ -100,6 +102,10 @@ def load() -> C.CDLL:
     lib.cfb_layer_timing.argtypes = [vp, i32, C.POINTER(i32), vp, vp, vp]
     lib.cfb_debug_net_forward_host.argtypes = [vp, vp, vp]
     lib.cfb_debug_conv3_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp]
+    lib.cfb_normalize_contrast_device.argtypes = [vp, i64, i64, i64, C.c_double, C.c_double, i32, i32, i32, vp]
+    lib.cfb_maskout_device.argtypes = [vp, i32, i64, i64, i64, i64, vp, i32, i64, i64, i64, vp]
+    lib.cfb_crop_margin_device.argtypes = [vp, i32, i64, i64, i64, i64, C.POINTER(i64 * 6), vp, vp]
+    lib.cfb_quantize_device.argtypes = [vp, i64, i64, i64, i64, i32, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("cfb_version", "cfb_device_count"):
@@ -115,6 +121,30 @@ def check(code: int) -> None:
 
 def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
+
+
+# ---- operators either side of `inference` on device pointers (include/chunkflow_b200.h) ----
+def normalize_contrast_device(d_image: int, zyx, lower_clip_fraction: float, upper_clip_fraction: float, minval: int,
+                              maxval: int, per_section: bool, stream: int = 0) -> None:
+    check(load().cfb_normalize_contrast_device(C.c_void_p(d_image), *(int(v) for v in zyx), float(lower_clip_fraction),
+                                               float(upper_clip_fraction), int(minval), int(maxval), int(bool(per_section)),
+                                               C.c_void_p(stream)))
+
+
+def maskout_device(d_chunk: int, chunk_dtype: int, czyx, d_mask: int, mask_dtype: int, factor, stream: int = 0) -> None:
+    check(load().cfb_maskout_device(C.c_void_p(d_chunk), int(chunk_dtype), *(int(v) for v in czyx), C.c_void_p(d_mask),
+                                    int(mask_dtype), *(int(v) for v in factor), C.c_void_p(stream)))
+
+
+def crop_margin_device(d_src: int, dtype: int, czyx, margin6, d_dst: int, stream: int = 0) -> None:
+    m = (C.c_int64 * 6)(*(int(v) for v in margin6))
+    check(load().cfb_crop_margin_device(C.c_void_p(d_src), int(dtype), *(int(v) for v in czyx), C.byref(m), C.c_void_p(d_dst),
+                                        C.c_void_p(stream)))
+
+
+def quantize_device(d_affinity: int, czyx, mode: int, d_out: int, stream: int = 0) -> None:
+    check(load().cfb_quantize_device(C.c_void_p(d_affinity), *(int(v) for v in czyx), int(mode), C.c_void_p(d_out),
+                                     C.c_void_p(stream)))
 
 
 def device_memory(device: int = 0) -> tuple:

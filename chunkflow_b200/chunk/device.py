@@ -1,0 +1,142 @@
+"""A chunk that lives in GPU memory between operators.
+
+``DeviceChunk`` wraps a CUDA ``torch.Tensor`` (the memory container only) with the ``voxel_offset`` / ``voxel_size``
+bookkeeping of the reference's ``Chunk`` and mirrors, name for name, the reference methods that sit either side of the
+``inference`` operator in a pipeline -- each one a hand-written kernel behind the C ABI (``include/chunkflow_b200.h``,
+``csrc/operators.cu``), bit-identical to the reference's numpy code:
+
+    normalize_contrast   reference chunk/image/base.py:93-132          (Image)
+    maskout              reference chunk/base.py:811-829                (Chunk; ``mask.maskout(chunk)`` modifies ``chunk``)
+    crop_margin          reference chunk/base.py:691-726                (Chunk)
+    quantize             reference chunk/affinity_map/base.py:33-57     (AffinityMap)
+
+so that ``create-chunk | normalize-contrast | inference | crop-margin | quantize`` moves the image to the GPU once and
+brings a uint8 thumbnail (or nothing) back instead of the 12-byte-per-voxel affinity map.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .. import _native
+from ..lib.cartesian_coordinate import Cartesian, to_cartesian
+from .base import Chunk
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("chunkflow_b200.DeviceChunk needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def _dtype_code(t) -> int:
+    torch = _torch()
+    if t.dtype in (torch.uint8, torch.bool):
+        return _native.DTYPE_U8
+    if t.dtype == torch.float32:
+        return _native.DTYPE_F32
+    raise TypeError(f"DeviceChunk operators support uint8/bool and float32, got {t.dtype}")
+
+
+class DeviceChunk:
+    def __init__(self, tensor, voxel_offset=None, voxel_size=None, layer_type: Optional[str] = None):
+        torch = _torch()
+        assert isinstance(tensor, torch.Tensor) and tensor.is_cuda, "DeviceChunk wraps a CUDA tensor"
+        assert tensor.ndim in (3, 4)
+        self.tensor = tensor.contiguous()
+        self.voxel_offset = to_cartesian(voxel_offset) if voxel_offset is not None else Cartesian(0, 0, 0)
+        self.voxel_size = to_cartesian(voxel_size) if voxel_size is not None else None
+        self.layer_type = layer_type
+
+    # ---- host <-> device -------------------------------------------------------------------
+    @classmethod
+    def from_chunk(cls, chunk: Chunk, device="cuda:0") -> "DeviceChunk":
+        torch = _torch()
+        arr = np.ascontiguousarray(chunk.array)
+        return cls(torch.from_numpy(arr).to(device), voxel_offset=chunk.voxel_offset, voxel_size=chunk.voxel_size,
+                   layer_type=getattr(chunk, "_layer_type", None))
+
+    def to_chunk(self) -> Chunk:
+        return Chunk(self.tensor.cpu().numpy(), voxel_offset=self.voxel_offset, voxel_size=self.voxel_size)
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    @property
+    def dtype(self):
+        return self.tensor.dtype
+
+    def _czyx(self):
+        s = self.shape
+        return (1,) + s if len(s) == 3 else s
+
+    def _stream(self) -> int:
+        return _torch().cuda.current_stream(self.tensor.device).cuda_stream
+
+    def _on_device(self):
+        return _torch().cuda.device(self.tensor.device)
+
+    # ---- Image.normalize_contrast ---------------------------------------------------------
+    def normalize_contrast(self, lower_clip_fraction: float = 0.01, upper_clip_fraction: float = 0.01, minval: int = 1,
+                           maxval: int = 255, per_section: bool = True) -> None:
+        """In place, like the reference (including its quirks: the whole-array pass also runs after the per-section pass,
+        and ``per_section=False`` does nothing)."""
+        torch = _torch()
+        assert self.tensor.dtype == torch.uint8 and self.tensor.ndim == 3, "normalize_contrast works on a (z,y,x) uint8 image"
+        with self._on_device():
+            _native.normalize_contrast_device(self.tensor.data_ptr(), self.shape, lower_clip_fraction, upper_clip_fraction,
+                                              minval, maxval, per_section, self._stream())
+
+    # ---- Chunk.maskout: self is the MASK, ``chunk`` is modified in place ---------------------
+    def maskout(self, chunk: "DeviceChunk") -> None:
+        assert chunk.voxel_size is not None and self.voxel_size is not None  # reference chunk/base.py:814-815
+        assert all(m >= c for m, c in zip(self.voxel_size, chunk.voxel_size))
+        assert all(m % c == 0 for m, c in zip(self.voxel_size, chunk.voxel_size)), "the voxel size should be divisible"
+        factor = tuple(m // c for m, c in zip(self.voxel_size, chunk.voxel_size))
+        assert self.tensor.ndim == 3
+        assert tuple(chunk.shape[-3:]) == tuple(s * f for s, f in zip(self.shape, factor)), \
+            "chunk size must equal mask size times the voxel-size factor"
+        with self._on_device():
+            _native.maskout_device(chunk.tensor.data_ptr(), _dtype_code(chunk.tensor), chunk._czyx(), self.tensor.data_ptr(),
+                                   _dtype_code(self.tensor), factor, chunk._stream())
+
+    # ---- Chunk.crop_margin ----------------------------------------------------------------
+    def crop_margin(self, margin_size: Sequence[int]) -> "DeviceChunk":
+        torch = _torch()
+        m = tuple(int(v) for v in margin_size)
+        if len(m) == 3:
+            m6 = m + m
+        elif len(m) == 6:
+            m6 = m
+        else:
+            raise ValueError('only support 3 or 6 elements.')  # reference chunk/base.py:719
+        c, z, y, x = self._czyx()
+        out_sp = (z - m6[0] - m6[3], y - m6[1] - m6[4], x - m6[2] - m6[5])
+        out_shape = out_sp if self.tensor.ndim == 3 else (c,) + out_sp
+        dst = torch.empty(out_shape, dtype=self.tensor.dtype, device=self.tensor.device)
+        with self._on_device():
+            _native.crop_margin_device(self.tensor.data_ptr(), _dtype_code(self.tensor), (c, z, y, x), m6, dst.data_ptr(),
+                                       self._stream())
+        offset = tuple(o + mm for o, mm in zip(self.voxel_offset, m))  # the three lower margins (reference :721-722)
+        return DeviceChunk(dst, voxel_offset=offset, voxel_size=self.voxel_size)
+
+    # ---- AffinityMap.quantize -------------------------------------------------------------
+    def quantize(self, mode: str = 'xy') -> "DeviceChunk":
+        torch = _torch()
+        assert self.tensor.dtype == torch.float32 and self.tensor.ndim == 4, "quantize works on a (c,z,y,x) float32 affinity map"
+        if mode == 'xy':
+            code = _native.QUANTIZE_XY
+        elif mode == 'z':
+            code = _native.QUANTIZE_Z
+        else:
+            raise ValueError(f'only support xy and z mode, but got {mode}')
+        out = torch.empty(self.shape[1:], dtype=torch.uint8, device=self.tensor.device)
+        with self._on_device():
+            _native.quantize_device(self.tensor.data_ptr(), self.shape, code, out.data_ptr(), self._stream())
+        return DeviceChunk(out, voxel_offset=self.voxel_offset, voxel_size=self.voxel_size)
+
+    def __repr__(self):
+        return f"DeviceChunk(shape={self.shape}, dtype={self.dtype}, voxel_offset={tuple(self.voxel_offset)}, device={self.tensor.device})"

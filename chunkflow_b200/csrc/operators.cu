@@ -1,0 +1,383 @@
+// Operators either side of `inference`, on the device, so that a chunk can stay in HBM between
+// operators instead of crossing PCIe (the 12.9 GB affinity map of a 1024^3 chunk):
+//   upstream    normalize-contrast  reference chunk/image/base.py:30-132  (per-section histogram -> LUT -> apply, uint8)
+//   both sides  maskout             reference chunk/base.py:811-829       (multiply by a coarser mask, integer factor)
+//   downstream  crop-margin         reference chunk/base.py:691-726
+//   downstream  quantize            reference chunk/affinity_map/base.py:33-57 (affinity -> uint8 image)
+// All four are HBM-bound byte/float streams: 16-byte vector accesses, grid = a multiple of the SM count, no tensor cores.
+// Results are bit-identical to the reference's numpy code (oracle/operators_oracle.py, tests/golden/operators.npz),
+// including its quirks (normalize_contrast: the whole-array pass also runs after the per-section pass; 255-bin histograms).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "chunkflow_b200.h"
+#include "common.cuh"
+
+namespace cfb {
+namespace {
+
+int sm_count_ops() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    CFB_CUDA(cudaGetDevice(&dev));
+    CFB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+template <typename F>
+int guarded_op(F&& f) {
+  try {
+    return f();
+  } catch (const std::invalid_argument& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_INVALID_ARGUMENT;
+  } catch (const CudaError& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_CUDA;
+  } catch (const std::exception& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_UNSUPPORTED;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// normalize-contrast
+// ------------------------------------------------------------------------------------------
+// Per-section 256-bin histogram.  grid = (blocks per section, Z); shared-memory atomics per block, one global
+// atomic per non-empty bin per block.  Algorithmic traffic: 1 B read per voxel.
+__global__ void __launch_bounds__(256) section_hist_kernel(const uint8_t* __restrict__ img, int64_t section_elems,
+                                                           unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint8_t* sec = img + (int64_t)blockIdx.y * section_elems;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 16-byte body where the section start is 16-byte aligned, scalar head / tail otherwise
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(sec);
+  const int64_t head_want = (int64_t)((16 - (addr & 15)) & 15);
+  const int64_t head = section_elems < head_want ? section_elems : head_want;
+  const int64_t nvec = (section_elems - head) / 16;
+  const uint4* v = reinterpret_cast<const uint4*>(sec + head);
+  for (int64_t i = tid; i < nvec; i += stride) {
+    const uint4 q = __ldg(v + i);
+    const unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd(&sh[w[k] & 255u], 1u);
+      atomicAdd(&sh[(w[k] >> 8) & 255u], 1u);
+      atomicAdd(&sh[(w[k] >> 16) & 255u], 1u);
+      atomicAdd(&sh[w[k] >> 24], 1u);
+    }
+  }
+  for (int64_t i = tid; i < head; i += stride) atomicAdd(&sh[sec[i]], 1u);
+  for (int64_t i = head + nvec * 16 + tid; i < section_elems; i += stride) atomicAdd(&sh[sec[i]], 1u);
+  __syncthreads();
+  const unsigned int c = sh[threadIdx.x];
+  if (c) atomicAdd(&hist[(int64_t)blockIdx.y * 256 + threadIdx.x], (unsigned long long)c);
+}
+
+// Clamping values + lookup table of ONE histogram, exactly as the reference computes them (image/base.py:30-91):
+// cdf without bin 0, over 255 bins unless the value 255 occurs (np.bincount minlength=255), double-precision
+// fractions, float32 table arithmetic with separate (unfused) subtract / multiply, clip, round half to even.
+// Returns false when the reference returns None (lower == upper): no transform.
+__device__ bool build_lut(const unsigned long long* hist, double lower_clip, double upper_clip, int minval, int maxval,
+                          uint8_t* lut) {
+  const int nbins = hist[255] ? 256 : 255;
+  unsigned long long total = 0;
+  for (int i = 1; i < nbins; ++i) total += hist[i];
+  if (total == 0) return false;
+  int lower = 0, upper = 0;
+  unsigned long long cdf = 0;
+  bool lower_done = false, upper_done = false;
+  for (int i = 0; i < nbins && !(lower_done && upper_done); ++i) {
+    if (i) cdf += hist[i];
+    const double frac = __ddiv_rn((double)cdf, (double)total);
+    if (!lower_done) { if (frac > lower_clip) lower_done = true; else lower = i; }
+    if (!upper_done) { if (frac > 1.0 - upper_clip) upper_done = true; else upper = i; }
+  }
+  if (lower == upper) return false;
+  const float scale = __double2float_rn(__ddiv_rn((double)maxval, (double)upper - (double)lower));
+  for (int u = 0; u < 256; ++u) {
+    float t = __fmul_rn(__fsub_rn((float)u, (float)lower), scale);
+    t = fminf(fmaxf(t, (float)minval), (float)maxval);
+    lut[u] = (uint8_t)(int)rintf(t);
+  }
+  return true;
+}
+
+// One thread per section builds the section tables (identity where the reference applies none).
+__global__ void section_lut_kernel(const unsigned long long* __restrict__ hist, int Z, double lower_clip, double upper_clip,
+                                   int minval, int maxval, uint8_t* __restrict__ luts) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z >= Z) return;
+  uint8_t* lut = luts + (size_t)z * 256;
+  if (!build_lut(hist + (size_t)z * 256, lower_clip, upper_clip, minval, maxval, lut))
+    for (int u = 0; u < 256; ++u) lut[u] = (uint8_t)u;
+}
+
+// The reference's trailing whole-array pass (the for loop's else clause) sees the per-section RESULT.  Its histogram is
+// the section histograms pushed through the section tables -- no second pass over the data -- and its table is composed
+// into every section table, so that one apply pass produces the final values.  One block, 256 threads.
+__global__ void __launch_bounds__(256) compose_global_lut_kernel(const unsigned long long* __restrict__ hist, int Z,
+                                                                 double lower_clip, double upper_clip, int minval,
+                                                                 int maxval, uint8_t* __restrict__ luts) {
+  __shared__ unsigned long long g[256];
+  __shared__ uint8_t glut[256];
+  __shared__ int has;
+  g[threadIdx.x] = 0;
+  __syncthreads();
+  for (int z = 0; z < Z; ++z) {
+    const unsigned long long c = hist[(size_t)z * 256 + threadIdx.x];
+    if (c) atomicAdd(&g[luts[(size_t)z * 256 + threadIdx.x]], c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) has = build_lut(g, lower_clip, upper_clip, minval, maxval, glut) ? 1 : 0;
+  __syncthreads();
+  if (!has) return;
+  for (int z = 0; z < Z; ++z) {
+    uint8_t* lut = luts + (size_t)z * 256;
+    lut[threadIdx.x] = glut[lut[threadIdx.x]];
+  }
+}
+
+// out[i] = lut[section][img[i]] in place.  Algorithmic traffic: 1 B read + 1 B written per voxel.
+__global__ void __launch_bounds__(256) apply_lut_kernel(uint8_t* __restrict__ img, int64_t section_elems,
+                                                        const uint8_t* __restrict__ luts) {
+  __shared__ uint8_t lut[256];
+  lut[threadIdx.x] = luts[(size_t)blockIdx.y * 256 + threadIdx.x];
+  __syncthreads();
+  uint8_t* sec = img + (int64_t)blockIdx.y * section_elems;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(sec);
+  const int64_t head_want = (int64_t)((16 - (addr & 15)) & 15);
+  const int64_t head = section_elems < head_want ? section_elems : head_want;
+  const int64_t nvec = (section_elems - head) / 16;
+  uint4* v = reinterpret_cast<uint4*>(sec + head);
+  for (int64_t i = tid; i < nvec; i += stride) {
+    uint4 q = v[i];
+    unsigned int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      w[k] = (unsigned int)lut[w[k] & 255u] | ((unsigned int)lut[(w[k] >> 8) & 255u] << 8) |
+             ((unsigned int)lut[(w[k] >> 16) & 255u] << 16) | ((unsigned int)lut[w[k] >> 24] << 24);
+    v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int64_t i = tid; i < head; i += stride) sec[i] = lut[sec[i]];
+  for (int64_t i = head + nvec * 16 + tid; i < section_elems; i += stride) sec[i] = lut[sec[i]];
+}
+
+// ------------------------------------------------------------------------------------------
+// maskout: chunk[c, z, y, x] *= mask[z / fz, y / fy, x / fx]   (numpy in-place multiply, dtype of the chunk)
+// ------------------------------------------------------------------------------------------
+template <typename T, typename M>
+__device__ __forceinline__ T mul_as(T v, M m);
+template <> __device__ __forceinline__ uint8_t mul_as<uint8_t, uint8_t>(uint8_t v, uint8_t m) { return (uint8_t)(v * m); }
+template <> __device__ __forceinline__ float mul_as<float, uint8_t>(float v, uint8_t m) { return __fmul_rn(v, (float)m); }
+template <> __device__ __forceinline__ float mul_as<float, float>(float v, float m) { return __fmul_rn(v, m); }
+
+// One thread per 16 bytes of a row (x is the fastest axis); rows = channels * Z * Y.
+template <typename T, typename M>
+__global__ void __launch_bounds__(256) maskout_kernel(T* __restrict__ chunk, int64_t rows, int Z, int Y, int X,
+                                                      const M* __restrict__ mask, int MY, int MX, int fz, int fy, int fx) {
+  constexpr int V = 16 / sizeof(T);
+  const int xv = (X + V - 1) / V;
+  const int64_t total = rows * xv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / xv;
+    const int x0 = (int)(i - row * xv) * V;
+    const int y = (int)(row % Y), z = (int)((row / Y) % Z);
+    T* p = chunk + row * X + x0;
+    const M* mrow = mask + ((int64_t)(z / fz) * MY + (y / fy)) * MX;
+    if (x0 + V <= X && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      uint4 q = *reinterpret_cast<uint4*>(p);
+      T* e = reinterpret_cast<T*>(&q);
+#pragma unroll
+      for (int k = 0; k < V; ++k) e[k] = mul_as<T, M>(e[k], __ldg(mrow + (x0 + k) / fx));
+      *reinterpret_cast<uint4*>(p) = q;
+    } else {
+      for (int k = 0; k < V && x0 + k < X; ++k) p[k] = mul_as<T, M>(p[k], __ldg(mrow + (x0 + k) / fx));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// crop-margin: dst = src[..., lo_z : Z - hi_z, lo_y : Y - hi_y, lo_x : X - hi_x]  (dense copy of the sub-box)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) crop_kernel(const T* __restrict__ src, int64_t channels, int Z, int Y, int X, int lz,
+                                                   int ly, int lx, int OZ, int OY, int OX, T* __restrict__ dst) {
+  const int64_t total = channels * OZ * OY * (int64_t)OX;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % OX);
+    int64_t r = i / OX;
+    const int y = (int)(r % OY); r /= OY;
+    const int z = (int)(r % OZ);
+    const int64_t c = r / OZ;
+    dst[i] = __ldg(src + ((c * Z + (z + lz)) * Y + (y + ly)) * (int64_t)X + (x + lx));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// quantize: uint8(((a0 + a1) / 2) * 255) ('xy') or uint8(a_last * 255) ('z'); float32 arithmetic, C truncation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t to_u8(float v) { return (uint8_t)(int)v; }
+
+__global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ a0, const float* __restrict__ a1, int64_t n,
+                                                       uint8_t* __restrict__ out) {
+  const bool vec = ((reinterpret_cast<uintptr_t>(a0) | reinterpret_cast<uintptr_t>(a1)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 3) == 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nvec = vec ? n / 4 : 0;
+  for (int64_t i = tid; i < nvec; i += stride) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(a0) + i);
+    float4 q = p;
+    if (a1) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(a1) + i);
+      q.x = __fdiv_rn(__fadd_rn(p.x, s.x), 2.f); q.y = __fdiv_rn(__fadd_rn(p.y, s.y), 2.f);
+      q.z = __fdiv_rn(__fadd_rn(p.z, s.z), 2.f); q.w = __fdiv_rn(__fadd_rn(p.w, s.w), 2.f);
+    }
+    uchar4 o;
+    o.x = to_u8(__fmul_rn(q.x, 255.f)); o.y = to_u8(__fmul_rn(q.y, 255.f));
+    o.z = to_u8(__fmul_rn(q.z, 255.f)); o.w = to_u8(__fmul_rn(q.w, 255.f));
+    reinterpret_cast<uchar4*>(out)[i] = o;
+  }
+  for (int64_t i = nvec * 4 + tid; i < n; i += stride) {
+    float v = a0[i];
+    if (a1) v = __fdiv_rn(__fadd_rn(v, a1[i]), 2.f);
+    out[i] = to_u8(__fmul_rn(v, 255.f));
+  }
+}
+
+int grid_for(int64_t work_items, int threads = 256) {
+  const int64_t want = ceil_div64(work_items, threads);
+  const int64_t cap = (int64_t)sm_count_ops() * 8;  // 8 resident CTAs of 256 threads per SM
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, cap));
+}
+
+void check_dims(int64_t c, int64_t z, int64_t y, int64_t x) {
+  if (c < 1 || z < 1 || y < 1 || x < 1 || z > INT32_MAX || y > INT32_MAX || x > INT32_MAX)
+    throw std::invalid_argument("chunk dimensions must be positive and each spatial axis below 2^31");
+}
+
+}  // namespace
+}  // namespace cfb
+
+using namespace cfb;
+
+extern "C" {
+
+int cfb_normalize_contrast_device(void* d_image, int64_t z, int64_t y, int64_t x, double lower_clip_fraction,
+                                  double upper_clip_fraction, int32_t minval, int32_t maxval, int32_t per_section,
+                                  void* stream) {
+  return guarded_op([&]() -> int {
+    check_dims(1, z, y, x);
+    if (!d_image) throw std::invalid_argument("normalize_contrast: null image");
+    if (minval < 0 || maxval > 255 || minval > maxval) throw std::invalid_argument("normalize_contrast: need 0 <= minval <= maxval <= 255");
+    // reference image/base.py:113: with per_section=False NOTHING runs (the whole-array branch belongs to the for loop)
+    if (!per_section) return CFB_OK;
+    if (z > 65535) throw std::invalid_argument("normalize_contrast: at most 65535 sections per call");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t section = y * x;
+    unsigned long long* hist = nullptr;
+    uint8_t* luts = nullptr;
+    CFB_CUDA(cudaMallocAsync(&hist, (size_t)z * 256 * sizeof(unsigned long long), s));
+    CFB_CUDA(cudaMallocAsync(&luts, (size_t)z * 256, s));
+    CFB_CUDA(cudaMemsetAsync(hist, 0, (size_t)z * 256 * sizeof(unsigned long long), s));
+    const int per_sec = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(section, 256 * 64), ceil_div64((int64_t)sm_count_ops() * 8, z)));
+    const dim3 grid(per_sec, (unsigned)z);
+    section_hist_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(d_image), section, hist);
+    CFB_LAUNCH_CHECK();
+    section_lut_kernel<<<(unsigned)ceil_div64(z, 64), 64, 0, s>>>(hist, (int)z, lower_clip_fraction, upper_clip_fraction, minval, maxval, luts);
+    CFB_LAUNCH_CHECK();
+    compose_global_lut_kernel<<<1, 256, 0, s>>>(hist, (int)z, lower_clip_fraction, upper_clip_fraction, minval, maxval, luts);
+    CFB_LAUNCH_CHECK();
+    apply_lut_kernel<<<grid, 256, 0, s>>>(static_cast<uint8_t*>(d_image), section, luts);
+    CFB_LAUNCH_CHECK();
+    CFB_CUDA(cudaFreeAsync(hist, s));
+    CFB_CUDA(cudaFreeAsync(luts, s));
+    return CFB_OK;
+  });
+}
+
+int cfb_maskout_device(void* d_chunk, int32_t chunk_dtype, int64_t channels, int64_t z, int64_t y, int64_t x,
+                       const void* d_mask, int32_t mask_dtype, int64_t fz, int64_t fy, int64_t fx, void* stream) {
+  return guarded_op([&]() -> int {
+    check_dims(channels, z, y, x);
+    if (!d_chunk || !d_mask) throw std::invalid_argument("maskout: null pointer");
+    if (fz < 1 || fy < 1 || fx < 1 || z % fz || y % fy || x % fx)
+      throw std::invalid_argument("maskout: the chunk size must be the mask size times the integer voxel-size factor");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t rows = channels * z * y;
+    const int MY = (int)(y / fy), MX = (int)(x / fx);
+    if (chunk_dtype == CFB_DTYPE_U8 && mask_dtype == CFB_DTYPE_U8) {
+      maskout_kernel<uint8_t, uint8_t><<<grid_for(rows * ceil_div64(x, 16)), 256, 0, s>>>(
+          static_cast<uint8_t*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const uint8_t*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx);
+    } else if (chunk_dtype == CFB_DTYPE_F32 && mask_dtype == CFB_DTYPE_U8) {
+      maskout_kernel<float, uint8_t><<<grid_for(rows * ceil_div64(x, 4)), 256, 0, s>>>(
+          static_cast<float*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const uint8_t*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx);
+    } else if (chunk_dtype == CFB_DTYPE_F32 && mask_dtype == CFB_DTYPE_F32) {
+      maskout_kernel<float, float><<<grid_for(rows * ceil_div64(x, 4)), 256, 0, s>>>(
+          static_cast<float*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const float*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx);
+    } else {
+      // numpy refuses uint8 *= float32 (casting rule 'same_kind'), and so do we
+      throw std::invalid_argument("maskout: unsupported dtype pair (chunk uint8 needs a uint8/bool mask)");
+    }
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  });
+}
+
+int cfb_crop_margin_device(const void* d_src, int32_t dtype, int64_t channels, int64_t z, int64_t y, int64_t x,
+                           const int64_t margin[6], void* d_dst, void* stream) {
+  return guarded_op([&]() -> int {
+    check_dims(channels, z, y, x);
+    if (!d_src || !d_dst || !margin) throw std::invalid_argument("crop_margin: null pointer");
+    for (int i = 0; i < 6; ++i)
+      if (margin[i] < 0) throw std::invalid_argument("crop_margin: negative margin");
+    const int64_t oz = z - margin[0] - margin[3], oy = y - margin[1] - margin[4], ox = x - margin[2] - margin[5];
+    if (oz < 1 || oy < 1 || ox < 1) throw std::invalid_argument("crop_margin: the margins leave nothing");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t total = channels * oz * oy * ox;
+    if (dtype == CFB_DTYPE_U8) {
+      crop_kernel<uint8_t><<<grid_for(total), 256, 0, s>>>(static_cast<const uint8_t*>(d_src), channels, (int)z, (int)y, (int)x,
+                                                          (int)margin[0], (int)margin[1], (int)margin[2], (int)oz, (int)oy, (int)ox,
+                                                          static_cast<uint8_t*>(d_dst));
+    } else if (dtype == CFB_DTYPE_F32) {
+      crop_kernel<float><<<grid_for(total), 256, 0, s>>>(static_cast<const float*>(d_src), channels, (int)z, (int)y, (int)x,
+                                                        (int)margin[0], (int)margin[1], (int)margin[2], (int)oz, (int)oy, (int)ox,
+                                                        static_cast<float*>(d_dst));
+    } else {
+      throw std::invalid_argument("crop_margin: dtype must be CFB_DTYPE_U8 or CFB_DTYPE_F32");
+    }
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  });
+}
+
+int cfb_quantize_device(const float* d_affinity, int64_t channels, int64_t z, int64_t y, int64_t x, int32_t mode,
+                        uint8_t* d_out, void* stream) {
+  return guarded_op([&]() -> int {
+    check_dims(channels, z, y, x);
+    if (!d_affinity || !d_out) throw std::invalid_argument("quantize: null pointer");
+    const int64_t n = z * y * x;
+    const float *a0, *a1;
+    if (mode == CFB_QUANTIZE_XY) {
+      if (channels < 2) throw std::invalid_argument("quantize: mode xy needs at least two channels");
+      a0 = d_affinity; a1 = d_affinity + n;
+    } else if (mode == CFB_QUANTIZE_Z) {
+      a0 = d_affinity + (channels - 1) * n; a1 = nullptr;
+    } else {
+      throw std::invalid_argument("quantize: only support xy and z mode");  // reference affinity_map/base.py:51
+    }
+    quantize_kernel<<<grid_for(ceil_div64(n, 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a0, a1, n, d_out);
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  });
+}
+
+}  // extern "C"

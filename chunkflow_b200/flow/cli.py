@@ -1,7 +1,8 @@
 """``chunkflow``-style command line for the inference hot path.
 
 Chained multi-command group with lazily pulled operator generators, like the reference
-(chunkflow/lib/flow.py:44-105).  Only the two commands on the hot path are provided:
+(chunkflow/lib/flow.py:44-105).  The two commands on the hot path, plus the operators either side of it on the GPU
+(`normalize-contrast`, `crop-margin`, `quantize`; `to-device` / `to-host` keep the chunk in GPU memory in between):
 
     python -m chunkflow_b200.flow.cli create-chunk --size 64 256 256 \
         inference --input-patch-size 20 256 256 --output-patch-overlap 4 64 64 \
@@ -124,7 +125,11 @@ def inference(tasks, name, convnet_model, convnet_weight_path, input_patch_size,
                 if "log" not in task:
                     task["log"] = {"timer": {}}
                 start = time()
-                task[output_chunk_name] = inferencer(task[input_chunk_name])
+                chunk_in = task[input_chunk_name]
+                if isinstance(chunk_in, Chunk) or inferencer.patch_inferencer is not None or state["dry_run"]:
+                    task[output_chunk_name] = inferencer(_to_host(chunk_in))
+                else:  # a DeviceChunk (see `to-device`): the result stays in GPU memory too
+                    task[output_chunk_name] = inferencer.infer_device(chunk_in)
                 task["log"]["timer"][name] = time() - start
                 task["log"]["compute_device"] = inferencer.compute_device
                 if state["verbose"]:
@@ -132,6 +137,118 @@ def inference(tasks, name, convnet_model, convnet_weight_path, input_patch_size,
                     print(f"{name}: {out.shape} in {task['log']['timer'][name]:.3f} s on "
                           f"{task['log']['compute_device']} ({np.prod(out.shape[-3:]) / task['log']['timer'][name] / 1e6:.1f} Mvoxels/s)")
             yield task
+
+
+# ---------------------------------------------------------------------------------------------
+# operators either side of `inference`, on the GPU.  A task's chunk is either a host
+# `Chunk` (moved to the GPU for the kernel and back, like `inference` does) or -- after `to-device` -- a `DeviceChunk`
+# that stays in GPU memory from operator to operator until `to-host`.
+# ---------------------------------------------------------------------------------------------
+def _to_host(chunk):
+    return chunk if isinstance(chunk, Chunk) else chunk.to_chunk()
+
+
+def _on_device(chunk, device):
+    """(DeviceChunk, was_host)"""
+    from chunkflow_b200.chunk.device import DeviceChunk
+    if isinstance(chunk, DeviceChunk):
+        return chunk, False
+    return DeviceChunk.from_chunk(chunk, device=device), True
+
+
+@main.command("to-device")
+@click.option("--device", type=str, default="cuda:0", help="GPU that will hold the chunk between operators.")
+@click.option("--input-chunk-name", "-i", type=str, default="chunk", help="input chunk name")
+@click.option("--output-chunk-name", "-o", type=str, default="chunk", help="output chunk name")
+@operator
+def to_device(tasks, device, input_chunk_name, output_chunk_name):
+    """(extension) Move the chunk to GPU memory; the following operators run on it there."""
+    for task in tasks:
+        if task is not None:
+            task[output_chunk_name] = _on_device(task[input_chunk_name], device)[0]
+        yield task
+
+
+@main.command("to-host")
+@click.option("--input-chunk-name", "-i", type=str, default="chunk", help="input chunk name")
+@click.option("--output-chunk-name", "-o", type=str, default="chunk", help="output chunk name")
+@operator
+def to_host(tasks, input_chunk_name, output_chunk_name):
+    """(extension) Bring a GPU-resident chunk back to host memory."""
+    for task in tasks:
+        if task is not None:
+            task[output_chunk_name] = _to_host(task[input_chunk_name])
+        yield task
+
+
+@main.command("normalize-contrast")
+@click.option("--name", type=str, default="normalize-contrast-nkem", help="name of operator.")
+@click.option("--input-chunk-name", "-i", type=str, default="chunk", help="input chunk name")
+@click.option("--output-chunk-name", "-o", type=str, default="chunk", help="output chunk name")
+@click.option("--lower-clip-fraction", "-l", type=click.FLOAT, default=0.01, help="lower intensity fraction to clip out.")
+@click.option("--upper-clip-fraction", "-u", type=click.FLOAT, default=0.01, help="upper intensity fraction to clip out.")
+@click.option("--minval", type=click.INT, default=1, help="the minimum intensity of transformed chunk.")
+@click.option("--maxval", type=click.INT, default=255, help="the maximum intensity of transformed chunk.")
+@click.option("--per-section/--whole", default=True, help="per section normalization or normalize the whole chunk.")
+@operator
+def normalize_contrast(tasks, name, input_chunk_name, output_chunk_name, lower_clip_fraction, upper_clip_fraction, minval,
+                       maxval, per_section):
+    """Normalize the section contrast (reference flow/flow.py:1672-1711, chunk/image/base.py:93-132)."""
+    import torch
+    from chunkflow_b200.chunk.device import DeviceChunk
+    for task in tasks:
+        if task is not None:
+            start = time()
+            dev, was_host = _on_device(task[input_chunk_name], "cuda:0")
+            if not was_host:  # the reference works on a clone (flow.py:1699)
+                dev = DeviceChunk(dev.tensor.clone(), voxel_offset=dev.voxel_offset, voxel_size=dev.voxel_size)
+            dev.normalize_contrast(lower_clip_fraction=lower_clip_fraction, upper_clip_fraction=upper_clip_fraction,
+                                   minval=minval, maxval=maxval, per_section=per_section)
+            torch.cuda.synchronize(dev.tensor.device)
+            task[output_chunk_name] = dev.to_chunk() if was_host else dev
+            task["log"]["timer"][name] = time() - start
+        yield task
+
+
+@main.command("crop-margin")
+@click.option("--name", type=str, default="crop-margin", help="name of this operator")
+@click.option("--margin-size", "-m", type=click.INT, nargs=6, default=None, callback=default_none,
+              help="crop the chunk margin: -z -y -x +z +y +x.")
+@click.option("--input-chunk-name", "-i", type=str, default="chunk", help="input chunk name.")
+@click.option("--output-chunk-name", "-o", type=str, default="chunk", help="output chunk name.")
+@operator
+def crop_margin(tasks, name, margin_size, input_chunk_name, output_chunk_name):
+    """Crop the margin of chunk (reference flow/flow.py:2053-2084; the bounding-box form needs a task bbox and is not
+    part of this path)."""
+    import torch
+    if not margin_size:
+        raise click.UsageError("crop-margin: --margin-size is required here (no task bounding boxes on this path)")
+    for task in tasks:
+        if task is not None:
+            start = time()
+            dev, was_host = _on_device(task[input_chunk_name], "cuda:0")
+            out = dev.crop_margin(margin_size)
+            torch.cuda.synchronize(out.tensor.device)
+            task[output_chunk_name] = out.to_chunk() if was_host else out
+            task["log"]["timer"][name] = time() - start
+        yield task
+
+
+@main.command("quantize")
+@click.option("--input-chunk-name", "-i", type=str, default="chunk", help="input chunk name")
+@click.option("--output-chunk-name", "-o", type=str, default="chunk", help="output chunk name")
+@click.option("--mode", type=click.Choice(["xy", "z"]), default="xy", help="xy: average of xy channel; z: only the z channel")
+@operator
+def quantize(tasks, input_chunk_name, output_chunk_name, mode):
+    """Transform an affinity map to a uint8 image (reference flow/flow.py:2250-2273, chunk/affinity_map/base.py:33-57)."""
+    import torch
+    for task in tasks:
+        if task is not None:
+            dev, was_host = _on_device(task[input_chunk_name], "cuda:0")
+            out = dev.quantize(mode=mode)
+            torch.cuda.synchronize(out.tensor.device)
+            task[output_chunk_name] = out.to_chunk() if was_host else out
+        yield task
 
 
 if __name__ == "__main__":

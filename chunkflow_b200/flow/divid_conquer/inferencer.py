@@ -295,6 +295,39 @@ class Inferencer(object):
             out = out[:-1]
         return Chunk(out, voxel_offset=output_voxel_offset, voxel_size=input_chunk.voxel_size)
 
+    def infer_device(self, input_chunk):
+        """Extension: the same operator on a :class:`chunkflow_b200.chunk.device.DeviceChunk` --
+        uint8 (or float32 in [0,1]) image already in GPU memory in, float32 affinity map in GPU memory out, nothing
+        crosses PCIe.  Built-in device backends only (``b200`` / ``identity``)."""
+        import torch
+        from chunkflow_b200.chunk.device import DeviceChunk
+        assert isinstance(input_chunk, DeviceChunk)
+        assert self.patch_inferencer is None, 'infer_device needs a built-in device backend (framework b200 / identity)'
+        t = input_chunk.tensor
+        if t.ndim == 4:
+            assert t.shape[0] == 1, 'one input channel'
+            t = t[0]
+        assert t.dtype in (torch.uint8, torch.float32)
+        assert t.device.index == self.engine.params.device, 'the chunk must live on the engine\'s GPU'
+        self._update_parameters_for_input_chunk(input_chunk)
+        output_voxel_offset = tuple(io + oc for io, oc in zip(input_chunk.voxel_offset, self.output_offset))
+        out = torch.empty(self.output_size, dtype=torch.float32, device=t.device)
+        try:
+            with torch.cuda.device(t.device):
+                stream = torch.cuda.current_stream(t.device)
+                self.engine.infer_chunk_device(t.data_ptr(), np.uint8 if t.dtype == torch.uint8 else np.float32,
+                                               tuple(t.shape), out.data_ptr(), stream.cuda_stream)
+                stream.synchronize()  # the range check of the result is reported by the call above
+            self.timing = self.engine.last_timing()
+        except _native.NativeError as err:
+            if err.code == _native.ERR_OUTPUT_RANGE:
+                raise AssertionError('output buffer should not be greater than 1') from err
+            raise
+        if self.mask_myelin_threshold:
+            assert out.shape[0] == 4
+            out = out[:-1]
+        return DeviceChunk(out, voxel_offset=output_voxel_offset, voxel_size=input_chunk.voxel_size)
+
     def _run_host_plugin(self, arr: np.ndarray, out: np.ndarray) -> None:
         """universal / prebuilt backends: device extract -> host callable -> device blend."""
         eng = self.engine

@@ -174,6 +174,41 @@ int cfb_debug_conv3_host(cfb_handle h, const float* h_in, int32_t cin, int32_t z
                          const float* h_weight, const float* h_bias, int32_t cout, int32_t relu,
                          float* h_out);
 
+/* ---------------------------------------------------------------------------------------------
+ * Operators either side of `inference`, on device memory: the chunk can stay in HBM
+ * between operators.  Stand-alone entry points (no handle); every pointer is a device pointer on the current
+ * device; work is enqueued on `stream` (a cudaStream_t, may be NULL).  Results are bit-identical to the reference's
+ * numpy code.  Python mirror: chunkflow_b200/chunk/device.py (DeviceChunk).
+ * ------------------------------------------------------------------------------------------- */
+#define CFB_QUANTIZE_XY 0
+#define CFB_QUANTIZE_Z 1
+
+/* In-place Image.normalize_contrast (reference chunk/image/base.py:30-132) of a (z,y,x) uint8 image: per-section
+ * 256-bin histogram (bin 0 ignored, 255 bins unless the value 255 occurs) -> clamping values at the clip fractions ->
+ * float32 lookup table clipped to [minval,maxval], rounded half to even -> applied; then, as in the reference (the
+ * whole-array branch is the `else` of its `for` loop), once more with the histogram of the WHOLE normalised array.
+ * per_section == 0 does nothing, exactly like the reference.  0 <= minval <= maxval <= 255. */
+int cfb_normalize_contrast_device(void* d_image, int64_t z, int64_t y, int64_t x, double lower_clip_fraction,
+                                  double upper_clip_fraction, int32_t minval, int32_t maxval, int32_t per_section,
+                                  void* stream);
+
+/* In-place Chunk.maskout (reference chunk/base.py:811-829): chunk[c,z,y,x] *= mask[z/fz, y/fy, x/fx], the mask being
+ * (z/fz, y/fy, x/fx) voxels at an integer multiple (fz,fy,fx) of the chunk's voxel size.  dtype pairs as numpy allows
+ * them in place: (U8 chunk, U8/bool mask), (F32 chunk, U8/bool mask), (F32 chunk, F32 mask). */
+int cfb_maskout_device(void* d_chunk, int32_t chunk_dtype, int64_t channels, int64_t z, int64_t y, int64_t x,
+                       const void* d_mask, int32_t mask_dtype, int64_t fz, int64_t fy, int64_t fx, void* stream);
+
+/* Chunk.crop_margin (reference chunk/base.py:691-726): d_dst (channels, z-m0-m3, y-m1-m4, x-m2-m5) receives
+ * src[..., m0:z-m3, m1:y-m4, m2:x-m5]; margin = {-z,-y,-x,+z,+y,+x} (the 3-element form is m3..5 = m0..2). */
+int cfb_crop_margin_device(const void* d_src, int32_t dtype, int64_t channels, int64_t z, int64_t y, int64_t x,
+                           const int64_t margin[6], void* d_dst, void* stream);
+
+/* AffinityMap.quantize (reference chunk/affinity_map/base.py:33-57): (channels,z,y,x) float32 -> (z,y,x) uint8,
+ * CFB_QUANTIZE_XY: uint8(((a[0] + a[1]) / 2) * 255), CFB_QUANTIZE_Z: uint8(a[channels-1] * 255); float32
+ * arithmetic, C truncation. */
+int cfb_quantize_device(const float* d_affinity, int64_t channels, int64_t z, int64_t y, int64_t x, int32_t mode,
+                        uint8_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,10 +80,19 @@ void launch_first_conv_umma(const void* chunk_u8, Int3 chunk_size, const PatchPo
 void launch_planar_to_cp8(const float* in, __half* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
 void launch_cp8_to_planar(const __half* in, float* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
 
+// Weights of the first layer as a kernel PARAMETER (1.8 KB in the constant bank): every FFMA takes its weight as a
+// constant-bank operand, so the kernel issues no shared-memory load for weights (it was LSU bound on those).
+struct FirstConvW {
+  float w[27][16];  // [tap][cout]
+  float b[16];
+};
+
 // First layer: extract `nb` patches from the uint8/f32 chunk (normalised by 1/255), 3x3x3
 // convolution 1 -> 16 in fp32 on CUDA cores, ReLU, CP8 output.  w: (16,1,3,3,3) fp32.
+// `cw` (host copy of the same weights) selects the constant-operand kernel; nullptr = weights staged in shared memory.
 void launch_first_conv_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb,
-                           Int3 patch, const float* w, const float* bias, __half* out, int parts, cudaStream_t s);
+                           Int3 patch, const float* w, const float* bias, __half* out, int parts, cudaStream_t s,
+                           const FirstConvW* cw = nullptr);
 // Same from already extracted fp32 patches (nb,1,Z,Y,X) (plugin level / debug).
 void launch_first_conv_cp8_from_patches(const float* patches, int nb, Int3 patch, const float* w, const float* bias,
                                         __half* out, int parts, cudaStream_t s);

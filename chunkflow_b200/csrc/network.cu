@@ -110,8 +110,14 @@ bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int 
     CFB_CUDA(cudaMemcpy(L.bias, bi->second.data(), bi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (umma() && sp.taps == 27 && sp.cin >= 16)
       pack_conv3_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
-    if (umma() && sp.taps == 27 && sp.cin == 1)
+    if (umma() && sp.taps == 27 && sp.cin == 1) {
       pack_first_conv_weights(wi->second.data(), bi->second.data(), parts(), L.packed);
+      if (cout == 16) {
+        for (int t = 0; t < 27; ++t)
+          for (int c = 0; c < 16; ++c) first_w_.w[t][c] = wi->second[(size_t)c * 27 + t];
+        for (int c = 0; c < 16; ++c) first_w_.b[c] = bi->second[c];
+      }
+    }
     if (umma() && sp.taps == 4)
       pack_convT_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
     layers_[sp.name] = L;
@@ -200,7 +206,8 @@ int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPo
     const ConvLayer& L = layers_.at("enc0.0");
     prof_begin("enc0.0", s);
     if (chunk && in_dtype == CFB_DTYPE_U8 && getenv("CFB_UMMA_FIRST_CONV")) launch_first_conv_umma(chunk, cs, patches, nb, s0, L.packed, h_e0a_, s);
-    else if (chunk) launch_first_conv_cp8(chunk, in_dtype, cs, patches, nb, s0, L.w, L.bias, h_e0a_, P, s);
+    else if (chunk) launch_first_conv_cp8(chunk, in_dtype, cs, patches, nb, s0, L.w, L.bias, h_e0a_, P, s,
+                                          getenv("CFB_FIRST_CONV_SMEM_W") ? nullptr : &first_w_);
     else launch_first_conv_cp8_from_patches(buf_in_, nb, s0, L.w, L.bias, h_e0a_, P, s);
     prof_end(s);
   }

@@ -73,6 +73,7 @@ class Network {
   int batch_ = 1;
   bool ready_ = false;
   int cnet_ = 0;
+  FirstConvW first_w_{};  // host copy of the first layer, passed to its kernel by value
   std::map<std::string, ConvLayer> layers_;
   std::vector<void*> owned_;
   // fp32 planar activations, (batch, C, Z, Y, X)

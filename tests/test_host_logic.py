@@ -130,3 +130,40 @@ def test_cli_accepts_every_reference_inference_flag():
     assert next(p for p in inference.params if p.name == "mask_output_chunk").default is False   # CLI default (ctor: True)
     assert next(p for p in inference.params if p.name == "output_patch_overlap").default == (4, 64, 64)
     assert "--size" in {o for p in create_chunk.params for o in p.opts}
+
+
+def test_cli_neighbour_operators_keep_the_reference_flags():
+    """normalize-contrast / crop-margin / quantize keep the reference's option surface
+    (flow/flow.py:1672-1687, 2053-2065, 2250-2256); to-device / to-host are the only additions."""
+    from chunkflow_b200.flow import cli
+
+    def opts(cmd):
+        return {o for p in cmd.params for o in p.opts + p.secondary_opts}
+
+    nc = opts(cli.normalize_contrast)
+    for flag in ["--name", "--input-chunk-name", "-i", "--output-chunk-name", "-o", "--lower-clip-fraction", "-l",
+                 "--upper-clip-fraction", "-u", "--minval", "--maxval", "--per-section", "--whole"]:
+        assert flag in nc, flag
+    defaults = {p.name: p.default for p in cli.normalize_contrast.params}
+    assert defaults["lower_clip_fraction"] == 0.01 and defaults["upper_clip_fraction"] == 0.01
+    assert defaults["minval"] == 1 and defaults["maxval"] == 255 and defaults["per_section"] is True
+    assert defaults["name"] == "normalize-contrast-nkem"
+    for flag in ["--name", "--margin-size", "-m", "--input-chunk-name", "-i", "--output-chunk-name", "-o"]:
+        assert flag in opts(cli.crop_margin), flag
+    assert next(p for p in cli.crop_margin.params if p.name == "margin_size").nargs == 6
+    q = opts(cli.quantize)
+    for flag in ["--input-chunk-name", "-i", "--output-chunk-name", "-o", "--mode"]:
+        assert flag in q, flag
+    assert set(next(p for p in cli.quantize.params if p.name == "mode").type.choices) == {"xy", "z"}
+    assert {"to-device", "to-host", "normalize-contrast", "crop-margin", "quantize", "inference", "create-chunk"} <= set(cli.main.commands)
+
+
+def test_device_chunk_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without CUDA the device-resident operators refuse to run."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only box")
+    from chunkflow_b200 import Chunk
+    from chunkflow_b200.chunk.device import DeviceChunk
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DeviceChunk.from_chunk(Chunk(np.zeros((2, 4, 4), np.uint8)))

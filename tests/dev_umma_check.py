@@ -1,4 +1,4 @@
-"""Development check of the tcgen05 path on a GPU box: every case runs in its own subprocess
+"""(test infrastructure -- it uses the oracle, so it lives under tests/)  Development check of the tcgen05 path on a GPU box: every case runs in its own subprocess
 with a timeout so that a trap / protocol bug cannot take the whole session down."""
 import json
 import os

@@ -87,73 +87,103 @@ __global__ void __launch_bounds__(256) section_hist_kernel(const uint8_t* __rest
 // Clamping values + lookup table of ONE histogram, exactly as the reference computes them (image/base.py:30-91):
 // cdf without bin 0, over 255 bins unless the value 255 occurs (np.bincount minlength=255), double-precision
 // fractions, float32 table arithmetic with separate (unfused) subtract / multiply, clip, round half to even.
-// Returns false when the reference returns None (lower == upper): no transform.
-__device__ bool build_lut(const unsigned long long* hist, double lower_clip, double upper_clip, int minval, int maxval,
-                          uint8_t* lut) {
-  const int nbins = hist[255] ? 256 : 255;
-  unsigned long long total = 0;
-  for (int i = 1; i < nbins; ++i) total += hist[i];
-  if (total == 0) return false;
-  int lower = 0, upper = 0;
-  unsigned long long cdf = 0;
-  bool lower_done = false, upper_done = false;
-  for (int i = 0; i < nbins && !(lower_done && upper_done); ++i) {
-    if (i) cdf += hist[i];
-    const double frac = __ddiv_rn((double)cdf, (double)total);
-    if (!lower_done) { if (frac > lower_clip) lower_done = true; else lower = i; }
-    if (!upper_done) { if (frac > 1.0 - upper_clip) upper_done = true; else upper = i; }
+// A block of 256 threads: thread 0 builds the prefix sums and finds both clamping values by binary search (the
+// fraction cdf / total is monotone in the bin index, so "the last bin before the first one whose fraction exceeds
+// the clip" -- the reference's two linear scans -- is a lower-bound search), then every thread writes one entry.
+// `has` = false where the reference returns None (lower == upper, or an empty histogram): no transform.
+struct LutScratch {
+  unsigned long long cdf[256];
+  int lower, upper, has;
+};
+
+__device__ __forceinline__ int first_fraction_above(const unsigned long long* cdf, int nbins, double total, double clip) {
+  int lo = 0, hi = nbins;  // first i with cdf[i] / total > clip; nbins if there is none
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ddiv_rn((double)cdf[mid], total) > clip) hi = mid; else lo = mid + 1;
   }
-  if (lower == upper) return false;
-  const float scale = __double2float_rn(__ddiv_rn((double)maxval, (double)upper - (double)lower));
-  for (int u = 0; u < 256; ++u) {
-    float t = __fmul_rn(__fsub_rn((float)u, (float)lower), scale);
-    t = fminf(fmaxf(t, (float)minval), (float)maxval);
-    lut[u] = (uint8_t)(int)rintf(t);
-  }
-  return true;
+  return lo;
 }
 
-// One thread per section builds the section tables (identity where the reference applies none).
-__global__ void section_lut_kernel(const unsigned long long* __restrict__ hist, int Z, double lower_clip, double upper_clip,
-                                   int minval, int maxval, uint8_t* __restrict__ luts) {
-  const int z = blockIdx.x * blockDim.x + threadIdx.x;
-  if (z >= Z) return;
-  uint8_t* lut = luts + (size_t)z * 256;
-  if (!build_lut(hist + (size_t)z * 256, lower_clip, upper_clip, minval, maxval, lut))
-    for (int u = 0; u < 256; ++u) lut[u] = (uint8_t)u;
+__device__ void build_lut_block(const unsigned long long* hist /* shared or global, 256 bins */, double lower_clip,
+                                double upper_clip, int minval, int maxval, LutScratch& sc, uint8_t* lut /* 256 entries */) {
+  if (threadIdx.x == 0) {
+    const int nbins = hist[255] ? 256 : 255;
+    unsigned long long acc = 0;
+    sc.cdf[0] = 0;  // bin 0 (pure black) carries no information (image/base.py:38)
+    for (int i = 1; i < nbins; ++i) { acc += hist[i]; sc.cdf[i] = acc; }
+    int lower = 0, upper = 0;
+    if (acc != 0) {
+      const double total = (double)acc;
+      int j = first_fraction_above(sc.cdf, nbins, total, lower_clip);
+      lower = j < nbins ? (j > 0 ? j - 1 : 0) : nbins - 1;
+      j = first_fraction_above(sc.cdf, nbins, total, 1.0 - upper_clip);
+      upper = j < nbins ? (j > 0 ? j - 1 : 0) : nbins - 1;
+    }
+    sc.lower = lower; sc.upper = upper; sc.has = lower != upper;
+  }
+  __syncthreads();
+  if (sc.has) {
+    const float scale = __double2float_rn(__ddiv_rn((double)maxval, (double)sc.upper - (double)sc.lower));
+    float t = __fmul_rn(__fsub_rn((float)threadIdx.x, (float)sc.lower), scale);
+    t = fminf(fmaxf(t, (float)minval), (float)maxval);
+    lut[threadIdx.x] = (uint8_t)(int)rintf(t);
+  }
+}
+
+// One block per section: section table (identity where the reference applies none).
+__global__ void __launch_bounds__(256) section_lut_kernel(const unsigned long long* __restrict__ hist, double lower_clip,
+                                                          double upper_clip, int minval, int maxval, uint8_t* __restrict__ luts) {
+  __shared__ unsigned long long h[256];
+  __shared__ LutScratch sc;
+  __shared__ uint8_t lut[256];
+  h[threadIdx.x] = hist[(size_t)blockIdx.x * 256 + threadIdx.x];
+  lut[threadIdx.x] = (uint8_t)threadIdx.x;
+  __syncthreads();
+  build_lut_block(h, lower_clip, upper_clip, minval, maxval, sc, lut);
+  luts[(size_t)blockIdx.x * 256 + threadIdx.x] = lut[threadIdx.x];
 }
 
 // The reference's trailing whole-array pass (the for loop's else clause) sees the per-section RESULT.  Its histogram is
-// the section histograms pushed through the section tables -- no second pass over the data -- and its table is composed
-// into every section table, so that one apply pass produces the final values.  One block, 256 threads.
-__global__ void __launch_bounds__(256) compose_global_lut_kernel(const unsigned long long* __restrict__ hist, int Z,
-                                                                 double lower_clip, double upper_clip, int minval,
-                                                                 int maxval, uint8_t* __restrict__ luts) {
-  __shared__ unsigned long long g[256];
-  __shared__ uint8_t glut[256];
-  __shared__ int has;
-  g[threadIdx.x] = 0;
-  __syncthreads();
-  for (int z = 0; z < Z; ++z) {
-    const unsigned long long c = hist[(size_t)z * 256 + threadIdx.x];
-    if (c) atomicAdd(&g[luts[(size_t)z * 256 + threadIdx.x]], c);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) has = build_lut(g, lower_clip, upper_clip, minval, maxval, glut) ? 1 : 0;
-  __syncthreads();
-  if (!has) return;
-  for (int z = 0; z < Z; ++z) {
-    uint8_t* lut = luts + (size_t)z * 256;
-    lut[threadIdx.x] = glut[lut[threadIdx.x]];
-  }
+// the section histograms pushed through the section tables -- no second pass over the data ...
+__global__ void __launch_bounds__(256) scatter_hist_kernel(const unsigned long long* __restrict__ hist,
+                                                           const uint8_t* __restrict__ luts, unsigned long long* __restrict__ g) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const unsigned long long c = hist[i];
+  if (c) atomicAdd(&g[luts[i]], c);
 }
 
-// out[i] = lut[section][img[i]] in place.  Algorithmic traffic: 1 B read + 1 B written per voxel.
+// ... its table (glut[256], glut[256] = 1 when there is one) ...
+__global__ void __launch_bounds__(256) global_lut_kernel(const unsigned long long* __restrict__ g, double lower_clip,
+                                                         double upper_clip, int minval, int maxval, uint8_t* __restrict__ glut) {
+  __shared__ unsigned long long h[256];
+  __shared__ LutScratch sc;
+  __shared__ uint8_t lut[256];
+  h[threadIdx.x] = g[threadIdx.x];
+  lut[threadIdx.x] = (uint8_t)threadIdx.x;
+  __syncthreads();
+  build_lut_block(h, lower_clip, upper_clip, minval, maxval, sc, lut);
+  glut[threadIdx.x] = lut[threadIdx.x];
+}
+
+// ... is composed into every section table, so that ONE apply pass produces the final values.
+__global__ void __launch_bounds__(256) compose_lut_kernel(const uint8_t* __restrict__ glut, uint8_t* __restrict__ luts) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  luts[i] = glut[luts[i]];
+}
+
+// out[i] = lut[section][img[i]] in place.  The table is replicated per lane (entry (value, lane) in bank `lane`), so
+// the 16 lookups of a thread never conflict.  Algorithmic traffic: 1 B read + 1 B written per voxel.
 __global__ void __launch_bounds__(256) apply_lut_kernel(uint8_t* __restrict__ img, int64_t section_elems,
                                                         const uint8_t* __restrict__ luts) {
-  __shared__ uint8_t lut[256];
-  lut[threadIdx.x] = luts[(size_t)blockIdx.y * 256 + threadIdx.x];
+  __shared__ unsigned int rep[256 * 32];
+  {
+    const unsigned int mine = luts[(size_t)blockIdx.y * 256 + threadIdx.x];
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) rep[threadIdx.x * 32 + ((j + threadIdx.x) & 31)] = mine;  // rotated: conflict-free writes
+  }
   __syncthreads();
+  const unsigned int* lut = rep + (threadIdx.x & 31);
   uint8_t* sec = img + (int64_t)blockIdx.y * section_elems;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,12 +197,12 @@ __global__ void __launch_bounds__(256) apply_lut_kernel(uint8_t* __restrict__ im
     unsigned int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      w[k] = (unsigned int)lut[w[k] & 255u] | ((unsigned int)lut[(w[k] >> 8) & 255u] << 8) |
-             ((unsigned int)lut[(w[k] >> 16) & 255u] << 16) | ((unsigned int)lut[w[k] >> 24] << 24);
+      w[k] = lut[(w[k] & 255u) << 5] | (lut[((w[k] >> 8) & 255u) << 5] << 8) | (lut[((w[k] >> 16) & 255u) << 5] << 16) |
+             (lut[(w[k] >> 24) << 5] << 24);
     v[i] = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  for (int64_t i = tid; i < head; i += stride) sec[i] = lut[sec[i]];
-  for (int64_t i = head + nvec * 16 + tid; i < section_elems; i += stride) sec[i] = lut[sec[i]];
+  for (int64_t i = tid; i < head; i += stride) sec[i] = (uint8_t)lut[(unsigned int)sec[i] << 5];
+  for (int64_t i = head + nvec * 16 + tid; i < section_elems; i += stride) sec[i] = (uint8_t)lut[(unsigned int)sec[i] << 5];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -184,31 +214,36 @@ template <> __device__ __forceinline__ uint8_t mul_as<uint8_t, uint8_t>(uint8_t 
 template <> __device__ __forceinline__ float mul_as<float, uint8_t>(float v, uint8_t m) { return __fmul_rn(v, (float)m); }
 template <> __device__ __forceinline__ float mul_as<float, float>(float v, float m) { return __fmul_rn(v, m); }
 
-// One block per row at a time (x is the fastest axis; grid = (rows of a plane, channel-planes)), one thread per 16 bytes:
-// no division per element -- the mask index advances incrementally.
+// Rows are the unit (x is the fastest axis; grid = (row groups of a plane, channel-planes)): `tpr` threads (a power of
+// two <= 256) cover one row with 16 bytes each, so a block works on 256 / tpr rows at a time -- narrow uint8 rows would
+// otherwise leave most of the block idle.  No division per element: the mask index advances incrementally.
 template <typename T, typename M>
 __global__ void __launch_bounds__(256) maskout_kernel(T* __restrict__ chunk, int64_t rows, int Z, int Y, int X,
-                                                      const M* __restrict__ mask, int MY, int MX, int fz, int fy, int fx) {
+                                                      const M* __restrict__ mask, int MY, int MX, int fz, int fy, int fx,
+                                                      int tpr) {
   constexpr int V = 16 / sizeof(T);
   const int64_t planes = rows / Y;  // channels * Z
+  const int rpb = 256 / tpr, rsub = threadIdx.x / tpr, tx = threadIdx.x % tpr;
   for (int64_t cz = blockIdx.y; cz < planes; cz += gridDim.y)
-  for (int y = blockIdx.x; y < Y; y += gridDim.x) {
+  for (int y = blockIdx.x * rpb + rsub; y < Y; y += gridDim.x * rpb) {
     const int z = (int)(cz % Z);
     T* prow = chunk + (cz * Y + y) * X;
     const M* mrow = mask + ((int64_t)(z / fz) * MY + (y / fy)) * MX;
     const bool aligned = (reinterpret_cast<uintptr_t>(prow) & 15) == 0;
-    for (int x0 = threadIdx.x * V; x0 < X; x0 += blockDim.x * V) {
+    for (int x0 = tx * V; x0 < X; x0 += tpr * V) {
       T* p = prow + x0;
       int q = x0 / fx, r = x0 - q * fx;
       if (aligned && x0 + V <= X) {
         uint4 pack = *reinterpret_cast<uint4*>(p);
-        T* e = reinterpret_cast<T*>(&pack);
-#pragma unroll
+        T e[V];
+        memcpy(e, &pack, 16);
         M m = __ldg(mrow + q);  // one mask load per run of fx voxels
+#pragma unroll
         for (int k = 0; k < V; ++k) {
           e[k] = mul_as<T, M>(e[k], m);
           if (++r == fx) { r = 0; ++q; if (k + 1 < V) m = __ldg(mrow + q); }
         }
+        memcpy(&pack, e, 16);
         *reinterpret_cast<uint4*>(p) = pack;
       } else {
         for (int k = 0; k < V && x0 + k < X; ++k) {
@@ -223,15 +258,16 @@ __global__ void __launch_bounds__(256) maskout_kernel(T* __restrict__ chunk, int
 // ------------------------------------------------------------------------------------------
 // crop-margin: dst = src[..., lo_z : Z - hi_z, lo_y : Y - hi_y, lo_x : X - hi_x]  (dense copy of the sub-box)
 // ------------------------------------------------------------------------------------------
-// One block per output row at a time; a row is OX * sizeof(T) contiguous bytes on both sides, copied with the widest
-// access the alignment of this row pair allows (16 B, 4 B or single elements).
+// Rows are the unit, `tpr` threads per row as above; a row is OX * sizeof(T) contiguous bytes on both sides, copied with
+// the widest access the alignment of this row pair allows (16 B, 4 B or single elements).
 template <typename T>
 __global__ void __launch_bounds__(256) crop_kernel(const T* __restrict__ src, int64_t channels, int Z, int Y, int X, int lz,
-                                                   int ly, int lx, int OZ, int OY, int OX, T* __restrict__ dst) {
+                                                   int ly, int lx, int OZ, int OY, int OX, T* __restrict__ dst, int tpr) {
   const int64_t planes = channels * OZ;
   const int row_bytes = OX * (int)sizeof(T);
+  const int rpb = 256 / tpr, rsub = threadIdx.x / tpr, tx = threadIdx.x % tpr;
   for (int64_t cz = blockIdx.y; cz < planes; cz += gridDim.y)
-  for (int y = blockIdx.x; y < OY; y += gridDim.x) {
+  for (int y = blockIdx.x * rpb + rsub; y < OY; y += gridDim.x * rpb) {
     const int z = (int)(cz % OZ);
     const int64_t c = cz / OZ;
     const T* s = src + ((c * Z + (z + lz)) * Y + (y + ly)) * (int64_t)X + lx;
@@ -240,13 +276,13 @@ __global__ void __launch_bounds__(256) crop_kernel(const T* __restrict__ src, in
     if ((both & 15) == 0) {
       const uint4* s4 = reinterpret_cast<const uint4*>(s);
       uint4* d4 = reinterpret_cast<uint4*>(d);
-      for (int i = threadIdx.x; i < row_bytes / 16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+      for (int i = tx; i < row_bytes / 16; i += tpr) d4[i] = __ldg(s4 + i);
     } else if ((both & 3) == 0) {
       const uint32_t* s1 = reinterpret_cast<const uint32_t*>(s);
       uint32_t* d1 = reinterpret_cast<uint32_t*>(d);
-      for (int i = threadIdx.x; i < row_bytes / 4; i += blockDim.x) d1[i] = __ldg(s1 + i);
+      for (int i = tx; i < row_bytes / 4; i += tpr) d1[i] = __ldg(s1 + i);
     } else {
-      for (int i = threadIdx.x; i < OX; i += blockDim.x) d[i] = __ldg(s + i);
+      for (int i = tx; i < OX; i += tpr) d[i] = __ldg(s + i);
     }
   }
 }
@@ -288,9 +324,16 @@ int grid_for(int64_t work_items, int threads = 256) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, cap));
 }
 
-dim3 grid_rows(int64_t planes, int64_t rows_per_plane) {  // row-per-block kernels: about 16 CTAs of 256 threads per SM
+int threads_per_row(int64_t row_bytes) {  // smallest power of two >= ceil(row_bytes / 16), at most 256
+  int t = 1;
+  while (t < 256 && (int64_t)t * 16 < row_bytes) t <<= 1;
+  return t;
+}
+
+dim3 grid_rows(int64_t planes, int64_t rows_per_plane, int tpr) {  // row kernels: about 16 CTAs of 256 threads per SM
   const int64_t gy = std::min<int64_t>(planes, 65535);
-  const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(rows_per_plane, ceil_div64((int64_t)sm_count_ops() * 16, gy)));
+  const int64_t groups = ceil_div64(rows_per_plane, 256 / tpr);
+  const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(groups, ceil_div64((int64_t)sm_count_ops() * 16, gy)));
   return dim3((unsigned)gx, (unsigned)gy);
 }
 
@@ -318,18 +361,24 @@ int cfb_normalize_contrast_device(void* d_image, int64_t z, int64_t y, int64_t x
     if (z > 65535) throw std::invalid_argument("normalize_contrast: at most 65535 sections per call");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t section = y * x;
-    unsigned long long* hist = nullptr;
-    uint8_t* luts = nullptr;
-    CFB_CUDA(cudaMallocAsync(&hist, (size_t)z * 256 * sizeof(unsigned long long), s));
-    CFB_CUDA(cudaMallocAsync(&luts, (size_t)z * 256, s));
-    CFB_CUDA(cudaMemsetAsync(hist, 0, (size_t)z * 256 * sizeof(unsigned long long), s));
-    const int per_sec = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(section, 256 * 64), ceil_div64((int64_t)sm_count_ops() * 8, z)));
+    unsigned long long* hist = nullptr;  // (z + 1) x 256: section histograms, then the whole-array histogram
+    uint8_t* luts = nullptr;             // (z + 1) x 256: section tables, then the whole-array table
+    CFB_CUDA(cudaMallocAsync(&hist, (size_t)(z + 1) * 256 * sizeof(unsigned long long), s));
+    CFB_CUDA(cudaMallocAsync(&luts, (size_t)(z + 1) * 256, s));
+    CFB_CUDA(cudaMemsetAsync(hist, 0, (size_t)(z + 1) * 256 * sizeof(unsigned long long), s));
+    unsigned long long* ghist = hist + (size_t)z * 256;
+    uint8_t* glut = luts + (size_t)z * 256;
+    const int per_sec = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(section, 256 * 64), ceil_div64((int64_t)sm_count_ops() * 6, z)));
     const dim3 grid(per_sec, (unsigned)z);
     section_hist_kernel<<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(d_image), section, hist);
     CFB_LAUNCH_CHECK();
-    section_lut_kernel<<<(unsigned)ceil_div64(z, 64), 64, 0, s>>>(hist, (int)z, lower_clip_fraction, upper_clip_fraction, minval, maxval, luts);
+    section_lut_kernel<<<(unsigned)z, 256, 0, s>>>(hist, lower_clip_fraction, upper_clip_fraction, minval, maxval, luts);
     CFB_LAUNCH_CHECK();
-    compose_global_lut_kernel<<<1, 256, 0, s>>>(hist, (int)z, lower_clip_fraction, upper_clip_fraction, minval, maxval, luts);
+    scatter_hist_kernel<<<(unsigned)z, 256, 0, s>>>(hist, luts, ghist);
+    CFB_LAUNCH_CHECK();
+    global_lut_kernel<<<1, 256, 0, s>>>(ghist, lower_clip_fraction, upper_clip_fraction, minval, maxval, glut);
+    CFB_LAUNCH_CHECK();
+    compose_lut_kernel<<<(unsigned)z, 256, 0, s>>>(glut, luts);
     CFB_LAUNCH_CHECK();
     apply_lut_kernel<<<grid, 256, 0, s>>>(static_cast<uint8_t*>(d_image), section, luts);
     CFB_LAUNCH_CHECK();
@@ -349,15 +398,16 @@ int cfb_maskout_device(void* d_chunk, int32_t chunk_dtype, int64_t channels, int
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int64_t rows = channels * z * y;
     const int MY = (int)(y / fy), MX = (int)(x / fx);
+    const int tpr = threads_per_row(x * (chunk_dtype == CFB_DTYPE_U8 ? 1 : 4));
     if (chunk_dtype == CFB_DTYPE_U8 && mask_dtype == CFB_DTYPE_U8) {
-      maskout_kernel<uint8_t, uint8_t><<<grid_rows(channels * z, y), 256, 0, s>>>(
-          static_cast<uint8_t*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const uint8_t*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx);
+      maskout_kernel<uint8_t, uint8_t><<<grid_rows(channels * z, y, tpr), 256, 0, s>>>(
+          static_cast<uint8_t*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const uint8_t*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx, tpr);
     } else if (chunk_dtype == CFB_DTYPE_F32 && mask_dtype == CFB_DTYPE_U8) {
-      maskout_kernel<float, uint8_t><<<grid_rows(channels * z, y), 256, 0, s>>>(
-          static_cast<float*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const uint8_t*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx);
+      maskout_kernel<float, uint8_t><<<grid_rows(channels * z, y, tpr), 256, 0, s>>>(
+          static_cast<float*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const uint8_t*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx, tpr);
     } else if (chunk_dtype == CFB_DTYPE_F32 && mask_dtype == CFB_DTYPE_F32) {
-      maskout_kernel<float, float><<<grid_rows(channels * z, y), 256, 0, s>>>(
-          static_cast<float*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const float*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx);
+      maskout_kernel<float, float><<<grid_rows(channels * z, y, tpr), 256, 0, s>>>(
+          static_cast<float*>(d_chunk), rows, (int)z, (int)y, (int)x, static_cast<const float*>(d_mask), MY, MX, (int)fz, (int)fy, (int)fx, tpr);
     } else {
       // numpy refuses uint8 *= float32 (casting rule 'same_kind'), and so do we
       throw std::invalid_argument("maskout: unsupported dtype pair (chunk uint8 needs a uint8/bool mask)");
@@ -377,14 +427,15 @@ int cfb_crop_margin_device(const void* d_src, int32_t dtype, int64_t channels, i
     const int64_t oz = z - margin[0] - margin[3], oy = y - margin[1] - margin[4], ox = x - margin[2] - margin[5];
     if (oz < 1 || oy < 1 || ox < 1) throw std::invalid_argument("crop_margin: the margins leave nothing");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int tpr = threads_per_row(ox * (dtype == CFB_DTYPE_U8 ? 1 : 4));
     if (dtype == CFB_DTYPE_U8) {
-      crop_kernel<uint8_t><<<grid_rows(channels * oz, oy), 256, 0, s>>>(static_cast<const uint8_t*>(d_src), channels, (int)z, (int)y, (int)x,
+      crop_kernel<uint8_t><<<grid_rows(channels * oz, oy, tpr), 256, 0, s>>>(static_cast<const uint8_t*>(d_src), channels, (int)z, (int)y, (int)x,
                                                           (int)margin[0], (int)margin[1], (int)margin[2], (int)oz, (int)oy, (int)ox,
-                                                          static_cast<uint8_t*>(d_dst));
+                                                          static_cast<uint8_t*>(d_dst), tpr);
     } else if (dtype == CFB_DTYPE_F32) {
-      crop_kernel<float><<<grid_rows(channels * oz, oy), 256, 0, s>>>(static_cast<const float*>(d_src), channels, (int)z, (int)y, (int)x,
+      crop_kernel<float><<<grid_rows(channels * oz, oy, tpr), 256, 0, s>>>(static_cast<const float*>(d_src), channels, (int)z, (int)y, (int)x,
                                                         (int)margin[0], (int)margin[1], (int)margin[2], (int)oz, (int)oy, (int)ox,
-                                                        static_cast<float*>(d_dst));
+                                                        static_cast<float*>(d_dst), tpr);
     } else {
       throw std::invalid_argument("crop_margin: dtype must be CFB_DTYPE_U8 or CFB_DTYPE_F32");
     }

@@ -273,7 +273,14 @@ def main():
     # ---- end to end through the public API: host uint8 chunk in -> host float32 affinity map out
     e2e = None
     if not args.no_e2e:
-        pin_out = torch.empty(out_shape, dtype=torch.float32, pin_memory=True)
+        need = int(np.prod(out_shape)) * 4
+        pin = True
+        try:  # page-locking 12.9 GB per rank: only when the host clearly has the room (all local ranks do the same)
+            import psutil
+            pin = psutil.virtual_memory().available > 3 * need * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        except Exception:
+            pass
+        pin_out = torch.empty(out_shape, dtype=torch.float32, pin_memory=pin)
         host_out = pin_out.numpy()
         chunk = Chunk(host_in)
         inf(chunk, output_buffer=host_out)  # warm-up (allocates the staging buffers)
@@ -286,6 +293,7 @@ def main():
         barrier()
         e2e = {"value": nvox * world * args.steps / dt / 1e6, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(host_in.nbytes),
                "d2h_bytes_per_step": int(host_out.nbytes), "ms_per_step": dt / args.steps * 1e3,
+               "host_buffers": "pinned" if pin else "pageable (not enough free host memory to page-lock the output)",
                "timing_of_last_step_ms": {k: round(v, 3) for k, v in inf.timing.items()}}
         del pin_out
 

@@ -25,12 +25,29 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    """sha256 over the native sources, the header and the compiler flags (file copies do not always keep mtimes)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, "include", "chunkflow_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "chunkflow_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(HASH_PATH) as f:
+            return f.read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build_variant(name: str, defines) -> str:
@@ -62,6 +79,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    if not extra:  # a build with development defines must not pass for the product library
+        with open(HASH_PATH, "w") as f:
+            f.write(_source_hash())
+    elif os.path.exists(HASH_PATH):
+        os.remove(HASH_PATH)
     return LIB_PATH
 
 

@@ -252,7 +252,7 @@ int g_trace_left = 64;        // print at most this many launches
 #endif
 // Development instrumentation of the TMEM-shift kernel (build with CFB_NVCC_DEFINES=-DCFB_TS_TRACE): ablation switches
 // (-DCFB_TS_ABLATE + env CFB_ABLATE, results become wrong) and per-role mbarrier wait-cycle counters.  Compiled out of the product build:
-// the single MMA-issuing thread is issue bound and even a predicate test per MMA costs ~20 %.
+// with one MMA-issuing thread the kernel was issue bound and even a predicate test per MMA cost ~20 %.
 #ifdef CFB_TS_ABLATE
 #define CFB_ABL(p, bit) (((p).ablate & (bit)) != 0)
 #else

@@ -80,3 +80,36 @@ def test_against_real_reference(seed):
         a, o = OP.crop_margin(aff, (3, 2, 1), margin)
         np.testing.assert_array_equal(a, np.asarray(r.array))
         assert tuple(o) == tuple(r.voxel_offset)
+
+
+@pytest.mark.skipif(not H.available(), reason="/root/reference not present (GPU box)")
+def test_normalize_contrast_property_against_real_reference():
+    """Randomised shapes, clip fractions and output ranges (hypothesis, bounded): oracle == real reference, bit for bit,
+    including degenerate histograms (empty, single value, value 255 present / absent)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    H.import_reference()
+    warnings.simplefilter("ignore")
+    from chunkflow.chunk.image.base import Image
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(1, 4), st.integers(1, 24), st.integers(1, 24), st.integers(0, 2 ** 31 - 1),
+           st.sampled_from([0.0, 0.01, 0.1, 0.5, 0.9, 1.0]), st.sampled_from([0.0, 0.01, 0.1, 0.5, 1.0]),
+           st.integers(0, 40), st.integers(41, 255), st.sampled_from(["uniform", "dark", "top", "const", "zero"]))
+    def check(z, y, x, seed, lo, hi, mn, mx, kind):
+        rng = np.random.default_rng(seed)
+        if kind == "uniform":
+            img = rng.integers(0, 256, (z, y, x), dtype=np.uint8)
+        elif kind == "dark":
+            img = rng.integers(0, 12, (z, y, x), dtype=np.uint8)
+        elif kind == "top":
+            img = rng.integers(250, 256, (z, y, x), dtype=np.uint8)
+        elif kind == "const":
+            img = np.full((z, y, x), rng.integers(0, 256), np.uint8)
+        else:
+            img = np.zeros((z, y, x), np.uint8)
+        im = Image(img.copy())
+        with redirect_stdout(io.StringIO()), redirect_stderr(io.StringIO()):
+            im.normalize_contrast(lo, hi, mn, mx, True)
+        np.testing.assert_array_equal(OP.normalize_contrast(img, lo, hi, mn, mx, True), np.asarray(im.array))
+
+    check()

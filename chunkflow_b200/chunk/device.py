@@ -40,6 +40,32 @@ def _dtype_code(t) -> int:
     raise TypeError(f"DeviceChunk operators support uint8/bool and float32, got {t.dtype}")
 
 
+def mask_array_for(chunk_dtype, mask: np.ndarray) -> np.ndarray:
+    """Host-side conversion of a mask of any dtype numpy accepts in ``chunk *= mask`` (reference chunk/base.py:811-829)
+    to one of the two mask dtypes the kernel takes, WITHOUT changing the result:
+
+    * uint8 chunk: numpy multiplies in the wider unsigned type and casts back modulo 256, which equals multiplying by
+      ``mask mod 256`` -> uint8 mask (signed / float masks are refused by numpy's 'same_kind' rule, and here);
+    * float32 chunk: an integer mask is converted by numpy to float64, the product rounded to float32; for |mask| < 2**24
+      that is the float32 product with the exactly converted mask -> float32 mask.  float64 masks are refused (the
+      double-precision product does not round like a float32 one)."""
+    chunk_dtype = np.dtype(chunk_dtype)
+    mask = np.asarray(mask)
+    if mask.dtype in (np.dtype(np.uint8), np.dtype(bool)) or (mask.dtype == np.float32 and chunk_dtype == np.float32):
+        return np.ascontiguousarray(mask)
+    if chunk_dtype == np.uint8:
+        if mask.dtype.kind != "u":
+            raise TypeError(f"numpy cannot cast {mask.dtype} to uint8 in place (same_kind); neither do we")
+        return np.ascontiguousarray(mask.astype(np.uint8))  # wraps modulo 256
+    if chunk_dtype == np.float32:
+        if mask.dtype.kind not in "ui":
+            raise TypeError(f"a {mask.dtype} mask on a float32 chunk is not supported (product rounds differently)")
+        if mask.size and int(np.abs(mask.astype(np.int64)).max()) >= 2 ** 24:
+            raise TypeError("integer mask values must be below 2**24 to be exact in float32")
+        return np.ascontiguousarray(mask.astype(np.float32))
+    raise TypeError(f"unsupported chunk dtype {chunk_dtype}")
+
+
 class DeviceChunk:
     def __init__(self, tensor, voxel_offset=None, voxel_size=None, layer_type: Optional[str] = None):
         torch = _torch()
@@ -57,6 +83,15 @@ class DeviceChunk:
         arr = np.ascontiguousarray(chunk.array)
         return cls(torch.from_numpy(arr).to(device), voxel_offset=chunk.voxel_offset, voxel_size=chunk.voxel_size,
                    layer_type=getattr(chunk, "_layer_type", None))
+
+    @classmethod
+    def mask_from_chunk(cls, mask: Chunk, like: "DeviceChunk") -> "DeviceChunk":
+        """A mask chunk of any numpy dtype (the reference's own test uses uint32) for ``maskout`` of ``like``:
+        converted on the host by :func:`mask_array_for`, then uploaded to ``like``'s GPU."""
+        torch = _torch()
+        target = np.uint8 if like.tensor.dtype == torch.uint8 else np.float32
+        arr = mask_array_for(target, mask.array)
+        return cls(torch.from_numpy(arr).to(like.tensor.device), voxel_offset=mask.voxel_offset, voxel_size=mask.voxel_size)
 
     def to_chunk(self) -> Chunk:
         return Chunk(self.tensor.cpu().numpy(), voxel_offset=self.voxel_offset, voxel_size=self.voxel_size)

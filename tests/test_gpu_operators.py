@@ -179,3 +179,25 @@ def test_cli_device_resident_chain_equals_host_chain():
     assert tuple(a.voxel_offset) == tuple(b.voxel_offset) == (1, 4, 4)
     assert np.abs(a.array.astype(int) - b.array.astype(int)).max() <= 1
     assert "normalize-contrast-nkem" in r_dev.return_value[0]["log"]["timer"]
+
+
+def test_reference_test_maskout_uint32_mask():
+    """Port of the reference's tests/chunk/test_chunk.py:65-76 (a uint32 mask at voxel size (2,4,8) on a uint8 image and a
+    float32 affinity map at (1,1,1)); the mask is converted on the host by DeviceChunk.mask_from_chunk."""
+    from chunkflow_b200.chunk.device import DeviceChunk
+    mask = np.ones((8, 16, 4), dtype=np.uint32)
+    mask[:4, :8, :2] = 0
+    mask = Chunk(mask, voxel_offset=(-2, -3, -4), voxel_size=(2, 4, 8))
+    rng = np.random.default_rng(0)
+    image = _dev(rng.integers(1, 256, size=(16, 64, 32), dtype=np.uint8), voxel_size=(1, 1, 1))
+    before = image.to_chunk().array
+    DeviceChunk.mask_from_chunk(mask, like=image).maskout(image)
+    got = image.to_chunk().array
+    np.testing.assert_array_equal(got[:8, :32, :16], 0)
+    np.testing.assert_array_equal(got, OP.maskout(mask.array, (2, 4, 8), before, (1, 1, 1)))
+    affs = _dev(rng.random((3, 16, 64, 32), dtype=np.float32) + 0.5, voxel_size=(1, 1, 1))
+    before = affs.to_chunk().array
+    DeviceChunk.mask_from_chunk(mask, like=affs).maskout(affs)
+    got = affs.to_chunk().array
+    np.testing.assert_array_equal(got[:, :8, :32, :16], 0)
+    np.testing.assert_array_equal(got, OP.maskout(mask.array, (2, 4, 8), before, (1, 1, 1)))

@@ -167,3 +167,30 @@ def test_device_chunk_fails_loudly_without_a_gpu():
     from chunkflow_b200.chunk.device import DeviceChunk
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DeviceChunk.from_chunk(Chunk(np.zeros((2, 4, 4), np.uint8)))
+
+
+def test_mask_conversion_preserves_numpy_semantics():
+    """chunkflow_b200.chunk.device.mask_array_for: masks of any dtype numpy accepts in `chunk *= mask` map onto the two
+    kernel mask dtypes without changing the result (reference tests/chunk/test_chunk.py:65-76 uses a uint32 mask)."""
+    from chunkflow_b200.chunk.device import mask_array_for
+    from oracle import operators_oracle as OP
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(4, 8, 12), dtype=np.uint8)
+    aff = rng.standard_normal((3, 4, 8, 12)).astype(np.float32)
+    for mdt, hi in ((np.uint32, 1000), (np.uint16, 700), (np.uint64, 5), (bool, 2), (np.uint8, 256)):
+        mask = rng.integers(0, hi, size=(2, 4, 3)).astype(mdt)
+        conv = mask_array_for(np.uint8, mask)
+        assert conv.dtype in (np.uint8, np.bool_)
+        np.testing.assert_array_equal(OP.maskout(conv, (2, 2, 4), img, (1, 1, 1)), OP.maskout(mask, (2, 2, 4), img, (1, 1, 1)))
+    for mdt, lo, hi in ((np.uint32, 0, 2 ** 24), (np.int32, -1000, 1000), (np.int64, -3, 3), (np.uint16, 0, 65536)):
+        mask = rng.integers(lo, hi, size=(2, 4, 3)).astype(mdt)
+        conv = mask_array_for(np.float32, mask)
+        assert conv.dtype == np.float32
+        np.testing.assert_array_equal(OP.maskout(conv, (2, 2, 4), aff, (1, 1, 1)), OP.maskout(mask, (2, 2, 4), aff, (1, 1, 1)))
+    for bad_chunk, bad_mask in ((np.uint8, np.ones((1, 1, 1), np.int32)), (np.uint8, np.ones((1, 1, 1), np.float32)),
+                                (np.float32, np.ones((1, 1, 1), np.float64)), (np.float32, np.full((1, 1, 1), 2 ** 24, np.int64))):
+        with pytest.raises(TypeError):
+            mask_array_for(bad_chunk, bad_mask)
+    # numpy itself refuses the first two of those
+    with pytest.raises(TypeError):
+        a = np.ones(3, np.uint8); a *= np.ones(3, np.int32)

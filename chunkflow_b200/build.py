@@ -34,6 +34,8 @@ def _source_hash() -> str:
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, "include", "chunkflow_b200.h")]
     for d in deps:
+        if not os.path.isfile(d):
+            continue
         h.update(os.path.basename(d).encode())
         with open(d, "rb") as f:
             h.update(f.read())

@@ -93,26 +93,170 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(chunk_shape, patch, overlap, n_patches, seed, threads):
-    """Times the reference algorithm (oracle port: torch-CPU network + numpy extract/blend) on the
-    first `n_patches` patches of the workload; returns seconds per patch incl. extract and blend."""
+def host_threads():
+    """Physical cores this process may use (SMT siblings oversubscribe the torch-CPU convolutions: the round-1 number
+    swung 3x between two identical boxes with os.cpu_count() threads)."""
+    n = os.cpu_count() or 1
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or n
+    except Exception:
+        n = max(1, n // 2)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+class CpuReference:
+    """The reference algorithm on the host cores (oracle port: torch-CPU network + numpy extract / blend / normalise,
+    bit-identical to the reference's `-f pytorch` CPU path, tests/test_oracle_vs_reference.py) on a sub-chunk that holds
+    `n_patches` whole patches of the workload's geometry.
+
+    Outside the timed region, as SURVEY.md section 8d / BASELINE.md section 3 define the metric: model load, patch mask
+    and output-chunk mask (built once per process / chunk shape by the reference, inferencer.py:300-312), the synthetic
+    input, one warm-up patch.  Inside: `/255` of the sub-chunk, per patch cutout + network + crop/mask + blend, the final
+    `*= 1/W` and the `< 1.0001` scan."""
+
+    def __init__(self, patch, overlap, threads):
+        import torch
+        from chunkflow_b200.lib import load_source
+        from oracle import inferencer_oracle as O
+        self.O, self.patch, self.overlap, self.threads = O, patch, overlap, threads
+        torch.set_num_threads(threads)
+        self.model = load_source(MODEL_FILE).load_model(None)
+        self.pmask = O.make_patch_mask(patch, overlap)
+        self.masks = {}
+        self.warm = False
+
+    def sub_chunk(self, chunk_shape, n_patches):
+        nx = min(n_patches, 2)
+        nz = (n_patches + nx - 1) // nx
+        sub = (self.patch[0] + (nz - 1) * (self.patch[0] - self.overlap[0]), self.patch[1],
+               self.patch[2] + (nx - 1) * (self.patch[2] - self.overlap[2]))
+        return tuple(min(a, c) for a, c in zip(sub, chunk_shape))
+
+    def run(self, chunk_shape, n_patches, seed):
+        """-> dict(seconds, patches, sub, per-part seconds, output, image)"""
+        O = self.O
+        sub = self.sub_chunk(chunk_shape, n_patches)
+        img = np.random.default_rng(seed).integers(0, 256, size=sub, dtype=np.uint8)
+        kw = dict(input_patch_size=self.patch, output_patch_overlap=self.overlap, num_output_channels=3, framework="pytorch",
+                  model=self.model)
+        if sub not in self.masks:
+            geom = O.Geometry(self.patch, None, self.overlap)
+            slices = O.patch_slices_list(geom, sub)
+            self.masks[sub] = (self.pmask, O.output_chunk_mask(geom, slices, sub, (0, 0, 0), self.pmask), len(slices))
+        if not self.warm:   # one warm-up patch (thread pool, oneDNN primitive cache)
+            O.infer_chunk(img[:self.patch[0], :self.patch[1], :self.patch[2]], patch_limit=1, precomputed=None, **kw)
+            self.warm = True
+        timers = {}
+        t0 = time.perf_counter()
+        out, _ = O.infer_chunk(img, precomputed=self.masks[sub][:2], timers=timers, **kw)
+        dt = time.perf_counter() - t0
+        return dict(seconds=dt, patches=self.masks[sub][2], sub=sub, parts=timers, output=out, image=img)
+
+
+def extrapolate_cpu(run, chunk_shape, P):
+    """Seconds for the whole chunk from a sample: per-patch parts scale with the patch count, per-voxel parts (the /255
+    of the input, the final normalise + range scan) with the chunk volume."""
+    nvox, svox = float(np.prod(chunk_shape)), float(np.prod(run["sub"]))
+    t = run["parts"]
+    per_patch = (t["network"] + t["extract_blend"]) / run["patches"]
+    per_voxel = (t["normalize_input"] + t["finalize"]) / svox
+    other = max(0.0, run["seconds"] - sum(t.values())) / run["patches"]   # python glue between the timers
+    return (per_patch + other) * P + per_voxel * nvox, per_patch, t["network"] / run["patches"]
+
+
+SPLIT_CHUNK = (512, 2048, 2048)   # BASELINE config #5 (zyx), 2541 patches of 32x256x256
+
+
+def split_chunk_block(inf, Chunk, patch, overlap, rank, world, local_rank, args, barrier, max_over_ranks):
+    """One oversized chunk over all ranks (chunkflow_b200.distributed.infer_chunk_split): z-slabs of patch rows, partial sums
+    of the overlapping planes sent to their owner over NCCL, added by cfb_halo_add_device, normalised by the owner.  Timed
+    with host buffers in (each rank uploads its sub-chunk inside the timed region) and the result left on the GPUs; then the
+    parts are gathered on rank 0 and compared with the single-GPU result of the same chunk."""
     import torch
-    from chunkflow_b200.lib import load_source
-    from oracle import inferencer_oracle as O
-    torch.set_num_threads(threads)
-    model = load_source(MODEL_FILE).load_model(None)
-    # a sub-chunk that holds n_patches whole patches of the real geometry (same patch size / overlap)
-    nx = min(n_patches, 2)
-    nz = (n_patches + nx - 1) // nx
-    sub = (patch[0] + (nz - 1) * (patch[0] - overlap[0]), patch[1], patch[2] + (nx - 1) * (patch[2] - overlap[2]))
-    sub = tuple(min(s, c) for s, c in zip(sub, chunk_shape))
-    rng = np.random.default_rng(seed)
-    img = rng.integers(0, 256, size=sub, dtype=np.uint8)
-    t0 = time.perf_counter()
-    out, _, parts = O.infer_chunk(img, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
-                                  framework="pytorch", model=model, return_parts=True)
-    dt = time.perf_counter() - t0
-    return dt / len(parts["slices"]), len(parts["slices"]), sub
+    import torch.distributed as dist
+    from chunkflow_b200 import distributed as D
+    shape = SPLIT_CHUNK
+    img = np.empty(shape, np.uint8)
+    for z in range(0, shape[0], 64):   # same data on every rank
+        img[z:z + 64] = np.random.default_rng(20260922 + 1000 + z).integers(0, 256, size=img[z:z + 64].shape, dtype=np.uint8)
+    chunk = Chunk(img)
+    slabs = D.plan_z_slabs(shape[0], patch[0], overlap[0], world)
+    tm = {}
+    part = D.infer_chunk_split(inf, chunk, to_host=False, timing=tm)   # warm-up (autotune for this rank's batch shapes)
+    del part
+    n_steps = min(args.steps, 3)
+    times, tms = [], []
+    for _ in range(n_steps):
+        barrier()
+        t0 = time.perf_counter()
+        tm = {}
+        part = D.infer_chunk_split(inf, chunk, to_host=False, timing=tm)
+        torch.cuda.synchronize()
+        times.append(max_over_ranks(time.perf_counter() - t0))
+        tms.append(tm)
+        if _ < n_steps - 1:
+            del part
+    exch = max_over_ranks(float(np.mean([t.get("exchange_ms", 0.0) for t in tms])))
+    comp = max_over_ranks(float(np.mean([t.get("compute_ms", 0.0) for t in tms])))
+    sent = torch.tensor([float(tms[-1].get("halo_bytes_sent", 0))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(sent)
+    # ---- gather on rank 0 and compare with the single-GPU result of the same chunk
+    C = 3
+    max_abs = None
+    me = slabs[rank]
+    if rank == 0:
+        full = torch.empty((C,) + shape, dtype=torch.float32, device="cuda")
+        if part is not None:
+            full[:, me.own_z0:me.own_z1] = part.tensor
+        for s in slabs[1:]:
+            if s.empty or s.own_z1 <= s.own_z0:
+                continue
+            for c in range(C):
+                dist.recv(full[c, s.own_z0:s.own_z1], src=s.rank)
+        del part
+        single = torch.empty((C,) + shape, dtype=torch.float32, device="cuda")
+        d_in = torch.from_numpy(img).cuda()
+        inf.engine.infer_chunk_device(d_in.data_ptr(), np.uint8, shape, single.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        max_abs = 0.0
+        for c in range(C):
+            for z in range(0, shape[0], 64):
+                max_abs = max(max_abs, float((full[c, z:z + 64] - single[c, z:z + 64]).abs().max().item()))
+        del full, single, d_in
+    else:
+        if part is not None:
+            t = part.tensor
+            for c in range(C):
+                dist.send(t[c].contiguous(), dst=0)
+        del part
+    torch.cuda.empty_cache()
+    barrier()
+    sec = float(np.mean(times))
+    nv = float(np.prod(shape))
+    return {"workload": f"ONE {'x'.join(map(str, shape))} uint8 chunk split into z-slabs of patch rows over {world} GPUs, "
+                        f"patch {'x'.join(map(str, patch))} overlap {'x'.join(map(str, overlap))}, host chunk in (H2D inside), result left on the GPUs",
+            "seconds": sec, "value": nv / sec / 1e6, "unit": "Mvoxels/s", "steps": n_steps, "ranks": world,
+            "rows_per_rank": [s.row_end - s.row_begin for s in slabs],
+            "halo_bytes_total": float(sent.item()), "exchange_ms_max_over_ranks": exch, "compute_ms_max_over_ranks": comp,
+            "exchange_share_of_step": exch / (sec * 1e3) if sec > 0 else None,
+            "exchange": "NCCL send/recv of the overlapping planes to their owner + cfb_halo_add_device; weight volume computed locally",
+            "max_abs_vs_single_gpu": max_abs, "tolerance": 2e-6}
 
 
 def main():
@@ -124,7 +268,10 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("CFB_BENCH_WORKLOAD", "1024"), choices=sorted(WORKLOADS))
     ap.add_argument("--batch-size", type=int, default=int(os.environ.get("CFB_BENCH_BATCH", 12)))
     ap.add_argument("--precision", default=os.environ.get("CHUNKFLOW_B200_PRECISION"))
-    ap.add_argument("--cpu-sample-patches", type=int, default=4)
+    ap.add_argument("--cpu-sample-patches", type=int, default=0, help="patches per CPU sample (0 = 12 for the cpu_baseline leg; the "
+                    "reference arm spreads >= 26 patches over its timed steps)")
+    ap.add_argument("--no-split-chunk", action="store_true", help="N > 1: skip the config-#5 block (one chunk split over the ranks)")
+    ap.add_argument("--no-pageable", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -135,7 +282,7 @@ def main():
     chunk_shape, patch, overlap = WORKLOADS[args.workload]
     nvox = int(np.prod(chunk_shape))
     P = patch_count(chunk_shape, patch, overlap)
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     config = {"workload": f"{'x'.join(map(str, chunk_shape))} uint8 chunk per GPU, 3-ch affinity UNet3L(16,32,64), "
                           f"patch {'x'.join(map(str, patch))} overlap {'x'.join(map(str, overlap))}, mask_output_chunk",
               "patches_per_chunk": P, "batch_size": args.batch_size, "chunks": world,
@@ -146,20 +293,29 @@ def main():
         # The reference's own CPU algorithm on the host cores (oracle port; /root/reference does not travel).
         if rank != 0:
             return
-        per_step = []
+        ref = CpuReference(patch, overlap, threads)
+        per_step = args.cpu_sample_patches or int(min(14, max(2, -(-26 // max(1, args.steps)))))
+        runs = []
         for i in range(args.warmup + args.steps):
-            spp, n, sub = cpu_reference_sample(chunk_shape, patch, overlap, args.cpu_sample_patches, 20260922 + i, threads)
-            if i >= args.warmup:
-                per_step.append(spp)
-        spp = float(np.mean(per_step))
-        value = nvox / (spp * P) / 1e6
-        sample = (f"{n} patches of {'x'.join(map(str, patch))} (sub-chunk {'x'.join(map(str, sub))}) per step incl. numpy extract/"
-                  f"blend/normalise; extrapolated by patch count to {P} patches")
+            timed = i >= args.warmup
+            r = ref.run(chunk_shape, per_step if timed else 1, 20260922 + i)   # a warm-up step is one patch
+            if timed:
+                runs.append(r)
+        agg = dict(seconds=sum(r["seconds"] for r in runs), patches=sum(r["patches"] for r in runs), sub=runs[0]["sub"],
+                   parts={k: sum(r["parts"][k] for r in runs) for k in runs[0]["parts"]})
+        agg["sub"] = (runs[0]["sub"][0] * len(runs),) + tuple(runs[0]["sub"][1:])   # voxels of all timed sub-chunks
+        total_s, per_patch, net_per_patch = extrapolate_cpu(agg, chunk_shape, P)
+        value = nvox / total_s / 1e6
+        sample = (f"{agg['patches']} patches of {'x'.join(map(str, patch))} timed over {len(runs)} steps (sub-chunk "
+                  f"{'x'.join(map(str, runs[0]['sub']))} per step): {per_patch:.3f} s/patch ({net_per_patch:.3f} s torch-CPU network + "
+                  f"{per_patch - net_per_patch:.3f} s numpy cutout/blend), per-voxel /255 + normalise + range scan scaled by volume; "
+                  f"extrapolated to {P} patches; excluded: model load, patch-mask and output-chunk-mask construction, one warm-up patch")
         print(json.dumps({
             "impl": "reference", "metric": "Mvoxels/s", "value": value, "unit": "Mvoxels/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * n * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": agg["seconds"] / len(runs) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Mvoxels/s", "cores": threads, "kind": "port", "sample": sample,
+                             "cpu": cpu_model(), "s_per_patch": per_patch, "s_per_patch_network": net_per_patch},
             "e2e": {"value": value, "unit": "Mvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -297,12 +453,51 @@ def main():
                "timing_of_last_step_ms": {k: round(v, 3) for k, v in inf.timing.items()}}
         del pin_out
 
-    cpu = None
+    # ---- the contract a drop-in caller gets: plain (pageable) numpy chunk in, `inf(chunk)` allocates its own result
+    e2e_pageable = None
+    if not args.no_e2e and not args.no_pageable:
+        plain = np.array(host_in, copy=True)   # ordinary pageable memory
+        chunk = Chunk(plain)
+        res = inf(chunk)                       # warm-up (creates the engine's pinned staging ring)
+        del res
+        barrier()
+        n_steps = min(args.steps, 3)
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            res = inf(chunk)                   # a fresh 12.9 GB np.empty per call, like the reference (inferencer.py:360,479)
+            checksum = float(res.array[0, -1, -1, -1])
+            del res
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_pageable = {"value": nvox * world * n_steps / dt / 1e6, "unit": "Mvoxels/s", "ms_per_step": dt / n_steps * 1e3,
+                        "steps": n_steps, "host_buffers": "pageable numpy in, result allocated by the call (np.empty) and filled "
+                        "through the engine's pinned staging ring by host threads", "last_value": checksum}
+        del plain, chunk
+
+    # ---- CPU baseline (rank 0, N = 1) and parity of the GPU path on the SAME sub-chunk at the benchmarked geometry
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        spp, n, sub = cpu_reference_sample(chunk_shape, patch, overlap, args.cpu_sample_patches, 20260922, threads)
-        cpu = {"value": nvox / (spp * P) / 1e6, "unit": "Mvoxels/s", "cores": threads, "kind": "port",
-               "sample": f"{n} patches of {'x'.join(map(str, patch))} (sub-chunk {'x'.join(map(str, sub))}), torch-CPU network + "
-                         f"numpy extract/blend/normalise, {spp:.3f} s/patch extrapolated to {P} patches"}
+        ref = CpuReference(patch, overlap, threads)
+        r = ref.run(chunk_shape, args.cpu_sample_patches or 12, 20260922)
+        total_s, per_patch, net_per_patch = extrapolate_cpu(r, chunk_shape, P)
+        cpu = {"value": nvox / total_s / 1e6, "unit": "Mvoxels/s", "cores": threads, "kind": "port", "cpu": cpu_model(),
+               "s_per_patch": per_patch, "s_per_patch_network": net_per_patch,
+               "sample": f"{r['patches']} patches of {'x'.join(map(str, patch))} (sub-chunk {'x'.join(map(str, r['sub']))}): {per_patch:.3f} s/patch "
+                         f"({net_per_patch:.3f} s torch-CPU network + {per_patch - net_per_patch:.3f} s numpy cutout/blend), per-voxel /255 + normalise + "
+                         f"range scan scaled by volume; extrapolated to {P} patches; excluded: model load, patch-mask and output-chunk-mask "
+                         "construction, one warm-up patch"}
+        got = inf(Chunk(r["image"])).array     # same Inferencer (batch, precision, autotuned tilings) as the timed steps
+        parity = {"max_abs": float(np.abs(got - r["output"]).max()), "tolerance": 1e-3,
+                  "config": f"sub-chunk {'x'.join(map(str, r['sub']))} = {r['patches']} patches of the benchmarked geometry, batch "
+                            f"{args.batch_size}, GPU result vs the CPU reference port (bit-identical to the reference's -f pytorch path)"}
+        del got, r
+
+    # ---- BASELINE config #5: ONE 512x2048x2048 chunk split over the N ranks, halo planes exchanged over NCCL
+    split = None
+    if world > 1 and not args.no_split_chunk:
+        del d_out
+        torch.cuda.empty_cache()
+        split = split_chunk_block(inf, Chunk, patch, overlap, rank, world, local_rank, args, barrier, max_over_ranks)
 
     if rank == 0:
         precision = {0: "f32 (FFMA, CUDA cores)", 1: "f16x3 hi/lo split on tcgen05, f32 accumulate",
@@ -312,6 +507,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {0: "f32", 1: "f16x3", 2: "f16"}[eng.params.precision], "precision_mode": precision,
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * args.steps,
+            "e2e_pageable": e2e_pageable, "parity": parity, "split_chunk": split,
             "roofline": roofline, "memory_kernels": mem, "kernel_ms_per_chunk": step_ms, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

@@ -17,6 +17,7 @@ ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED =
 FRAMEWORK_UNET3L, FRAMEWORK_IDENTITY = 0, 1
 PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA = 0, 1, 2
 DTYPE_U8, DTYPE_F32 = 0, 1
+AUGMENT_NONE, AUGMENT_REFERENCE, AUGMENT_SPATIAL = 0, 1, 2
 QUANTIZE_XY, QUANTIZE_Z = 0, 1
 
 # every symbol include/chunkflow_b200.h declares
@@ -24,6 +25,7 @@ EXPORTS = (
     "cfb_last_error", "cfb_version", "cfb_device_count", "cfb_device_memory", "cfb_create", "cfb_destroy", "cfb_device_name",
     "cfb_set_weight", "cfb_commit_weights", "cfb_patch_mask", "cfb_patch_grid", "cfb_output_shape",
     "cfb_infer_chunk_device", "cfb_infer_chunk_host", "cfb_infer_slab_device", "cfb_normalize_device",
+    "cfb_slab_nonzero", "cfb_halo_add_device", "cfb_weight_volume_device",
     "cfb_patch_forward_host", "cfb_make_patch_mask", "cfb_plugin_begin", "cfb_plugin_extract", "cfb_plugin_blend",
     "cfb_plugin_end", "cfb_last_timing", "cfb_set_profiling", "cfb_layer_timing", "cfb_debug_net_forward_host", "cfb_debug_conv3_host",
     "cfb_normalize_contrast_device", "cfb_maskout_device", "cfb_crop_margin_device", "cfb_quantize_device",
@@ -90,7 +92,10 @@ def load() -> C.CDLL:
     lib.cfb_infer_chunk_device.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp]
     lib.cfb_infer_chunk_host.argtypes = [vp, vp, i32, i64, i64, i64, vp]
     lib.cfb_infer_slab_device.argtypes = [vp, vp, i32, i64, i64, i64, i64, i64, vp, vp, vp]
-    lib.cfb_normalize_device.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
+    lib.cfb_normalize_device.argtypes = [vp, vp, vp, i32, i64, i64, i64, i64, i32, vp]
+    lib.cfb_slab_nonzero.argtypes = [vp, C.POINTER(i32), vp]
+    lib.cfb_halo_add_device.argtypes = [vp, vp, i64, vp]
+    lib.cfb_weight_volume_device.argtypes = [vp, i64, i64, i64, i64, i64, i32, vp, vp]
     lib.cfb_patch_forward_host.argtypes = [vp, vp, i32, vp]
     lib.cfb_make_patch_mask.argtypes = [C.POINTER(i32 * 3), C.POINTER(i32 * 3), vp]
     lib.cfb_plugin_begin.argtypes = [vp, vp, i32, i64, i64, i64]
@@ -163,6 +168,23 @@ def make_patch_mask(patch_size, overlap) -> np.ndarray:
     return out
 
 
+def augment_code(augment) -> int:
+    """``augment`` as the Inferencer takes it: falsy -> none; True / 'reference' -> the reference's literal arithmetic
+    (transform.py:30-52,147-156); 'spatial' -> the 8 spatial flip / transpose variants (explicit opt-in)."""
+    if not augment:
+        return AUGMENT_NONE
+    if augment is True or augment == "reference" or augment == AUGMENT_REFERENCE:
+        return AUGMENT_REFERENCE
+    if augment == "spatial" or augment == AUGMENT_SPATIAL:
+        return AUGMENT_SPATIAL
+    raise ValueError(f"augment must be False, True, 'reference' or 'spatial', not {augment!r}")
+
+
+def halo_add_device(d_dst: int, d_src: int, count: int, stream: int = 0) -> None:
+    """d_dst[i] += d_src[i] for `count` float32 on the current device (multi-GPU halo planes)."""
+    check(load().cfb_halo_add_device(C.c_void_p(d_dst), C.c_void_p(d_src), int(count), C.c_void_p(stream)))
+
+
 class Engine:
     """RAII wrapper of a ``cfb_handle``."""
 
@@ -180,8 +202,10 @@ class Engine:
         p.output_patch_overlap[:] = [int(v) for v in output_patch_overlap]
         p.output_crop_margin[:] = [int(v) for v in output_crop_margin]
         p.num_input_channels, p.num_output_channels = int(num_input_channels), int(num_output_channels)
-        p.batch_size, p.mask_output_chunk, p.augment = int(batch_size), int(bool(mask_output_chunk)), int(bool(augment))
-        p.has_myelin_threshold = int(mask_myelin_threshold is not None)
+        p.batch_size, p.mask_output_chunk = int(batch_size), int(bool(mask_output_chunk))
+        p.augment = augment_code(augment)
+        # truthiness, like the reference (inferencer.py:468: `if self.mask_myelin_threshold:`): None and 0.0 both mean "off"
+        p.has_myelin_threshold = int(bool(mask_myelin_threshold))
         p.mask_myelin_threshold = float(mask_myelin_threshold or 0.0)
         p.check_output_range = int(bool(check_output_range))
         self.params = p
@@ -257,12 +281,24 @@ class Engine:
                                               *(int(v) for v in chunk_zyx), int(zrow_begin), int(zrow_end),
                                               C.c_void_p(d_out), C.c_void_p(d_weight), C.c_void_p(stream)))
 
-    def normalize_device(self, d_out: int, d_weight: int, czyx, stream: int = 0) -> None:
-        check(self._lib.cfb_normalize_device(self._h, C.c_void_p(d_out), C.c_void_p(d_weight),
-                                             *(int(v) for v in czyx), C.c_void_p(stream)))
+    def normalize_device(self, d_out: int, d_weight: int, czyx, stream: int = 0, weight_is_inverse: bool = False,
+                         all_zero_input: bool = False) -> None:
+        check(self._lib.cfb_normalize_device(self._h, C.c_void_p(d_out), C.c_void_p(d_weight), int(bool(weight_is_inverse)),
+                                             *(int(v) for v in czyx), int(bool(all_zero_input)), C.c_void_p(stream)))
+
+    def slab_nonzero(self, stream: int = 0) -> bool:
+        flag = C.c_int32()
+        check(self._lib.cfb_slab_nonzero(self._h, C.byref(flag), C.c_void_p(stream)))
+        return bool(flag.value)
+
+    def weight_volume_device(self, chunk_zyx, z_begin: int, z_end: int, d_weight: int, invert: bool = False, stream: int = 0) -> None:
+        check(self._lib.cfb_weight_volume_device(self._h, *(int(v) for v in chunk_zyx), int(z_begin), int(z_end), int(bool(invert)),
+                                                 C.c_void_p(d_weight), C.c_void_p(stream)))
 
     def patch_forward_host(self, patches: np.ndarray) -> np.ndarray:
         patches = np.ascontiguousarray(patches, dtype=np.float32)
+        if patches.ndim != 5 or patches.shape[1:] != (1,) + self.input_patch_size:
+            raise ValueError(f"expected input patches of shape (batch, 1, {self.input_patch_size}), got {patches.shape}")
         b = patches.shape[0]
         out = np.empty((b, self.num_output_channels) + self.output_patch_size, np.float32)
         check(self._lib.cfb_patch_forward_host(self._h, _ptr(patches), b, _ptr(out)))
@@ -275,9 +311,19 @@ class Engine:
 
     def plugin_extract(self, first: int, nb: int, out: np.ndarray) -> None:
         assert out.dtype == np.float32 and out.flags.c_contiguous
+        if out.shape != (nb, 1) + self.input_patch_size:
+            raise ValueError(f"patch buffer must have shape {(nb, 1) + self.input_patch_size}, got {out.shape}")
         check(self._lib.cfb_plugin_extract(self._h, int(first), int(nb), _ptr(out)))
 
     def plugin_blend(self, first: int, nb: int, masked: np.ndarray) -> None:
+        """`masked`: what the user's patch backend returned for patches [first, first+nb) -- already cropped to the output
+        patch and bump-masked.  The native side reads nb*C*prod(output_patch_size) floats, so the shape is checked here
+        (the reference fails with a numpy broadcasting error on a wrong shape)."""
+        masked = np.asarray(masked)
+        want = (nb, self.num_output_channels) + self.output_patch_size
+        if masked.shape != want:
+            raise ValueError(f"the patch backend must return an array of shape {want} (batch, channels, cropped output patch); "
+                             f"got {masked.shape}")
         masked = np.ascontiguousarray(masked, dtype=np.float32)
         check(self._lib.cfb_plugin_blend(self._h, int(first), int(nb), _ptr(masked)))
 

@@ -38,8 +38,14 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct PatchPos {
   int iz, iy, ix;  // input patch start inside the chunk
   int oz, oy, ox;  // start of the (cropped) output patch inside the output buffer (may be <0 / clipped)
-  int flags;       // test-time augmentation variant: bit 0 transpose y<->x, bit 1 flip x, bit 2 flip y
+  int flags;       // test-time augmentation variant: bit 0 transpose y<->x, bit 1 flip x, bit 2 flip y,
+                   // bit 3 (kTtaChannelSym) blend the variant AND its channel-reversed copy
 };
+
+// Reference-literal --augment (transform.py:30-52,147-156): FlipLR / FlipUD act on the CHANNEL / BATCH axes of the
+// 5-D buffers, so the 8 "variants" of a patch are {identity, transpose} x {as is, output channels reversed} x 2
+// duplicates: two network evaluations, each blended together with its channel-reversed copy, weight 1/4.
+constexpr int kTtaChannelSym = 8;
 
 // Test-time augmentation (reference transform.py:114-145: transpose, then flip x, then flip y).
 // Maps coordinates (y, x) of the TRANSFORMED patch of size (Y, X) back to the original patch.

@@ -12,6 +12,7 @@
 
 #include "chunkflow_b200.h"
 #include "common.cuh"
+#include "host_stager.cuh"
 #include "kernels_memory.cuh"
 #include "kernels_simt.cuh"
 #include "network.cuh"
@@ -122,15 +123,25 @@ struct cfb_engine {
   float* d_plugin_in = nullptr; size_t plugin_in_cap = 0;
   bool plugin_active = false; int plugin_dtype = 0;
 
+  std::unique_ptr<HostStager> stager;  // pinned ring + host threads for results that go to pageable memory
+
   cudaEvent_t ev[8]{};
   bool timing_valid = false;
   int64_t launches = 0;
 
-  // reference transform.py:114-156: 8 augmented evaluations per patch, averaged
-  int variants() const { return (p.augment && p.framework == CFB_FRAMEWORK_UNET3L) ? 8 : 1; }
+  // reference transform.py:114-156: 8 augmented evaluations per patch, averaged.  CFB_AUGMENT_REFERENCE: the
+  // reference's flips act on the channel / batch axes, so its 8 variants are 2 network evaluations (identity,
+  // transpose), each blended with its channel-reversed copy (weight 1/4); CFB_AUGMENT_SPATIAL: 8 spatial variants.
+  int variants() const {
+    if (!p.augment || p.framework != CFB_FRAMEWORK_UNET3L) return 1;
+    return p.augment == CFB_AUGMENT_SPATIAL ? 8 : 2;
+  }
+  int variant_flags(int v) const { return (p.augment == CFB_AUGMENT_REFERENCE && variants() > 1) ? (v | kTtaChannelSym) : v; }
+  float variant_scale() const { return variants() == 1 ? 1.0f : (p.augment == CFB_AUGMENT_SPATIAL ? 0.125f : 0.25f); }
 
   ~cfb_engine() {
     cudaSetDevice(p.device);
+    stager.reset();
     net.release();
     cudaFree(d_mask); cudaFree(d_patches); cudaFree(d_cover); cudaFree(d_winv); cudaFree(d_flags);
     cudaFree(d_cover_z_slab); cudaFree(d_host_in); cudaFree(d_host_out); cudaFree(d_plugin_out); cudaFree(d_plugin_in);
@@ -184,7 +195,7 @@ void prepare_chunk(cfb_engine* e, int64_t cz, int64_t cy, int64_t cx, cudaStream
       for (size_t c = 0; c < e->gx.in_start.size(); ++c)
         for (int v = 0; v < e->variants(); ++v)  // 8 flip/transpose variants per patch with --augment
           e->h_patches.push_back(PatchPos{e->gz.in_start[a], e->gy.in_start[b], e->gx.in_start[c],
-                                          e->gz.out_start[a], e->gy.out_start[b], e->gx.out_start[c], v});
+                                          e->gz.out_start[a], e->gy.out_start[b], e->gx.out_start[c], e->variant_flags(v)});
   if (e->h_patches.empty()) throw std::invalid_argument("no patch fits the chunk");
   cudaFree(e->d_patches); e->d_patches = nullptr;
   CFB_CUDA(cudaMalloc(&e->d_patches, e->h_patches.size() * sizeof(PatchPos)));
@@ -234,7 +245,14 @@ struct Progressive {
   cudaEvent_t ready = nullptr;
   const float* winv = nullptr;
   int planes_done = 0;
+  HostStager* stager = nullptr;  // set when h_out is pageable memory
 };
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
 
 void flush_planes(cfb_engine* e, Progressive* pg, float* d_out, int z_end, cudaStream_t s) {
   if (z_end <= pg->planes_done) return;
@@ -243,11 +261,16 @@ void flush_planes(cfb_engine* e, Progressive* pg, float* d_out, int z_end, cudaS
   const int64_t off = (int64_t)pg->planes_done * plane, count = (int64_t)(z_end - pg->planes_done) * plane;
   launch_normalize(d_out + off, pg->winv ? pg->winv + off : nullptr, true, C, count, e->d_flags + 1, e->d_flags, s, nvox);
   e->launches++;
-  CFB_CUDA(cudaEventRecord(pg->ready, s));
-  CFB_CUDA(cudaStreamWaitEvent(pg->copy_stream, pg->ready, 0));
-  for (int c = 0; c < C; ++c)
-    CFB_CUDA(cudaMemcpyAsync(pg->h_out + c * nvox + off, d_out + c * nvox + off, (size_t)count * sizeof(float),
-                             cudaMemcpyDeviceToHost, pg->copy_stream));
+  if (pg->stager) {
+    for (int c = 0; c < C; ++c)
+      pg->stager->push(d_out + c * nvox + off, pg->h_out + c * nvox + off, (size_t)count * sizeof(float), s, pg->copy_stream);
+  } else {
+    CFB_CUDA(cudaEventRecord(pg->ready, s));
+    CFB_CUDA(cudaStreamWaitEvent(pg->copy_stream, pg->ready, 0));
+    for (int c = 0; c < C; ++c)
+      CFB_CUDA(cudaMemcpyAsync(pg->h_out + c * nvox + off, d_out + c * nvox + off, (size_t)count * sizeof(float),
+                               cudaMemcpyDeviceToHost, pg->copy_stream));
+  }
   pg->planes_done = z_end;
 }
 
@@ -258,7 +281,7 @@ void run_patches(cfb_engine* e, const void* d_in, int in_dtype, int64_t first, i
   const int C = e->p.num_output_channels;
   const int B = std::max(1, e->p.batch_size);
   const int64_t per_row = (int64_t)e->gy.in_start.size() * e->gx.in_start.size() * e->variants();
-  const float scale = 1.0f / (float)e->variants();
+  const float scale = e->variant_scale();
   for (int64_t i = first; i < last; i += B) {
     const int nb = (int)std::min<int64_t>(B, last - i);
     if (pg) {
@@ -307,7 +330,7 @@ int infer_impl(cfb_engine* e, const void* d_in, int in_dtype, int64_t cz, int64_
   CFB_CUDA(cudaEventRecord(e->ev[1], s));
   run_patches(e, d_in, in_dtype, zrow_begin * ny * nx * e->variants(), zrow_end * ny * nx * e->variants(), d_out, s, pg);
   CFB_CUDA(cudaEventRecord(e->ev[2], s));
-  if (slab) {
+  if (slab && d_weight) {
     // partial weight sum of this slab's patches only
     std::vector<int> cz_t;
     build_cover(e->gz, e->op.z, e->out_size.z, cz_t, (int)zrow_begin, (int)zrow_end);
@@ -317,6 +340,8 @@ int infer_impl(cfb_engine* e, const void* d_in, int in_dtype, int64_t cz, int64_
     launch_weight_volume(e->d_mask, e->op, e->d_cover_z_slab, e->d_cover_y, e->d_cover_x, e->d_oz0, e->d_oy0,
                          e->d_ox0, e->out_size, d_weight, /*invert=*/false, s);
     e->launches++;
+  } else if (slab) {
+    // no partial weight volume wanted: the owner of a plane computes the full weight sum itself (cfb_weight_volume_device)
   } else if (pg) {
     flush_planes(e, pg, d_out, e->out_size.z, s);  // remaining planes
   } else {
@@ -393,6 +418,8 @@ int cfb_create(const cfb_params* params, cfb_handle* out) {
     if (p.framework != CFB_FRAMEWORK_UNET3L && p.framework != CFB_FRAMEWORK_IDENTITY) throw std::invalid_argument("unknown framework");
     if (p.num_input_channels != 1) throw std::invalid_argument("only one input channel is supported");
     if (p.num_output_channels < 1 || p.num_output_channels > 8) throw std::invalid_argument("num_output_channels must be in [1, 8]");
+    if (p.augment != CFB_AUGMENT_NONE && p.augment != CFB_AUGMENT_REFERENCE && p.augment != CFB_AUGMENT_SPATIAL)
+      throw std::invalid_argument("augment must be CFB_AUGMENT_NONE / _REFERENCE / _SPATIAL");
     if (p.augment && p.framework == CFB_FRAMEWORK_UNET3L && p.input_patch_size[1] != p.input_patch_size[2])
       throw std::invalid_argument("test-time augmentation transposes y and x: the patch must be square in y, x");
     auto e = std::make_unique<cfb_engine>();
@@ -518,20 +545,87 @@ int cfb_infer_chunk_device(cfb_handle h, const void* d_in, int32_t in_dtype, int
 int cfb_infer_slab_device(cfb_handle h, const void* d_in, int32_t in_dtype, int64_t cz, int64_t cy, int64_t cx,
                           int64_t zrow_begin, int64_t zrow_end, float* d_out, float* d_weight, void* stream) {
   return guarded([&]() -> int {
-    if (!h || !d_in || !d_out || !d_weight) throw std::invalid_argument("null argument");
+    if (!h || !d_in || !d_out) throw std::invalid_argument("null argument");
     return infer_impl(h, d_in, in_dtype, cz, cy, cx, zrow_begin, zrow_end, true, d_out, d_weight, (cudaStream_t)stream);
   });
 }
 
-int cfb_normalize_device(cfb_handle h, float* d_out, const float* d_weight, int64_t channels, int64_t oz, int64_t oy,
-                         int64_t ox, void* stream) {
+int cfb_normalize_device(cfb_handle h, float* d_out, const float* d_weight, int32_t weight_is_inverse, int64_t channels,
+                         int64_t oz, int64_t oy, int64_t ox, int32_t all_zero_input, void* stream) {
   return guarded([&]() -> int {
     if (!h || !d_out) throw std::invalid_argument("null argument");
     CFB_CUDA(cudaSetDevice(h->p.device));
     cudaStream_t s = (cudaStream_t)stream;
-    CFB_CUDA(cudaMemsetAsync(h->d_flags + 1, 0, sizeof(unsigned int), s));
-    launch_normalize(d_out, d_weight, /*w_is_inverse=*/false, (int)channels, oz * oy * ox, h->d_flags + 1, nullptr, s);
+    // d_flags[0]: the nonzero flag the kernel reads (0 forces the output to zero, reference inferencer.py:387-393)
+    const unsigned int init[2] = {all_zero_input ? 0u : 1u, 0u};
+    CFB_CUDA(cudaMemcpyAsync(h->d_flags, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    launch_normalize(d_out, d_weight, weight_is_inverse != 0, (int)channels, oz * oy * ox, h->d_flags + 1, h->d_flags, s);
     if (h->p.has_myelin_threshold) launch_myelin_mask(d_out, (int)channels, oz * oy * ox, h->p.mask_myelin_threshold, s);
+    if (h->p.check_output_range) {
+      unsigned int flags[2];
+      CFB_CUDA(cudaMemcpyAsync(flags, h->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, s));
+      CFB_CUDA(cudaStreamSynchronize(s));
+      float vmax; std::memcpy(&vmax, &flags[1], 4);
+      if (!(vmax < 1.0001f)) {  // reference inferencer.py:465-466
+        set_last_error("output buffer should not be greater than 1 (max = " + std::to_string(vmax) + ")");
+        return CFB_ERR_OUTPUT_RANGE;
+      }
+    }
+    return CFB_OK;
+  });
+}
+
+int cfb_slab_nonzero(cfb_handle h, int32_t* nonzero, void* stream) {
+  return guarded([&]() -> int {
+    if (!h || !nonzero) throw std::invalid_argument("null argument");
+    CFB_CUDA(cudaSetDevice(h->p.device));
+    unsigned int flag = 0;
+    CFB_CUDA(cudaMemcpyAsync(&flag, h->d_flags, sizeof(flag), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CFB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *nonzero = flag != 0u;
+    return CFB_OK;
+  });
+}
+
+int cfb_halo_add_device(float* d_dst, const float* d_src, int64_t count, void* stream) {
+  return guarded([&]() -> int {
+    if (!d_dst || !d_src || count < 0) throw std::invalid_argument("bad argument");
+    launch_halo_add(d_dst, d_src, count, (cudaStream_t)stream);
+    return CFB_OK;
+  });
+}
+
+int cfb_weight_volume_device(cfb_handle h, int64_t cz, int64_t cy, int64_t cx, int64_t z_begin, int64_t z_end, int32_t invert,
+                             float* d_weight, void* stream) {
+  return guarded([&]() -> int {
+    if (!h || !d_weight) throw std::invalid_argument("null argument");
+    CFB_CUDA(cudaSetDevice(h->p.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cz < h->ip.z || cy < h->ip.y || cx < h->ip.x) throw std::invalid_argument("input chunk is smaller than the input patch");
+    const Int3 out{(int)cz - 2 * h->ocm.z, (int)cy - 2 * h->ocm.y, (int)cx - 2 * h->ocm.x};
+    if (z_begin < 0 || z_end > out.z || z_begin > z_end) throw std::invalid_argument("bad plane range");
+    const AxisGrid gz = axis_grid((int)cz, h->ip.z, h->ioverlap.z, h->istride.z, h->pcrop.z, h->ocm.z);
+    const AxisGrid gy = axis_grid((int)cy, h->ip.y, h->ioverlap.y, h->istride.y, h->pcrop.y, h->ocm.y);
+    const AxisGrid gx = axis_grid((int)cx, h->ip.x, h->ioverlap.x, h->istride.x, h->pcrop.x, h->ocm.x);
+    std::vector<int> tz, ty, tx, all;
+    build_cover(gz, h->op.z, out.z, tz);
+    build_cover(gy, h->op.y, out.y, ty);
+    build_cover(gx, h->op.x, out.x, tx);
+    for (const std::vector<int>* v : std::initializer_list<const std::vector<int>*>{&tz, &ty, &tx, &gz.out_start, &gy.out_start, &gx.out_start})
+      all.insert(all.end(), v->begin(), v->end());
+    int* d_tab = nullptr;
+    CFB_CUDA(cudaMalloc(&d_tab, all.size() * sizeof(int)));
+    cudaError_t err = cudaMemcpyAsync(d_tab, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (err == cudaSuccess) {
+      const int* cz_t = d_tab; const int* cy_t = cz_t + tz.size(); const int* cx_t = cy_t + ty.size();
+      const int* oz0 = cx_t + tx.size(); const int* oy0 = oz0 + gz.out_start.size(); const int* ox0 = oy0 + gy.out_start.size();
+      try {
+        launch_weight_volume(h->d_mask, h->op, cz_t, cy_t, cx_t, oz0, oy0, ox0, out, d_weight, invert != 0, s, (int)z_begin, (int)z_end);
+      } catch (...) { cudaStreamSynchronize(s); cudaFree(d_tab); throw; }
+      err = cudaStreamSynchronize(s);  // the tables are temporaries
+    }
+    cudaFree(d_tab);
+    CFB_CUDA(err);
     return CFB_OK;
   });
 }
@@ -556,13 +650,28 @@ int cfb_infer_chunk_host(cfb_handle h, const void* h_in, int32_t in_dtype, int64
     pg.h_out = h_out;
     pg.copy_stream = h->copy_stream;
     pg.ready = h->ev_ready;
+    // a result array in pageable memory (what a drop-in caller has: a fresh np.empty) is filled through the
+    // engine's own pinned ring by host threads; CFB_NO_HOST_STAGING=1 leaves the staging to the driver
+    static const bool no_staging = getenv("CFB_NO_HOST_STAGING") != nullptr;
+    if (!no_staging && out_bytes >= ((size_t)8 << 20) && !is_pinned_host(h_out)) {
+      if (!h->stager) h->stager = std::make_unique<HostStager>(h->p.device);
+      pg.stager = h->stager.get();
+    }
     const bool progressive = !h->p.has_myelin_threshold;
     rc = infer_impl(h, h->d_host_in, in_dtype, cz, cy, cx, 0, 0, false, h->d_host_out, nullptr, s, progressive ? &pg : nullptr);
-    if (rc != CFB_OK) { cudaStreamSynchronize(h->copy_stream); return rc; }
+    if (rc != CFB_OK) {
+      cudaStreamSynchronize(h->copy_stream);
+      if (pg.stager) { try { pg.stager->drain(); } catch (...) {} }
+      return rc;
+    }
     CFB_CUDA(cudaEventRecord(h->ev[6], s));
-    if (!progressive) CFB_CUDA(cudaMemcpyAsync(h_out, h->d_host_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    if (!progressive) {
+      if (pg.stager) pg.stager->push(h->d_host_out, h_out, out_bytes, s, h->copy_stream);
+      else CFB_CUDA(cudaMemcpyAsync(h_out, h->d_host_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    }
     CFB_CUDA(cudaEventRecord(h->ev[7], s));
     CFB_CUDA(cudaStreamSynchronize(s));
+    if (pg.stager) pg.stager->drain();
     CFB_CUDA(cudaStreamSynchronize(h->copy_stream));
     return CFB_OK;
   });

@@ -320,8 +320,10 @@ head_blend_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
     }
     const float m = __ldg(mask + ov) * scale;
     float* dst = out + ((size_t)gz * os.y + gy) * os.x + gx;
+    for (int co = 0; co < channels; ++co) acc[co] = __fdiv_rn(1.0f, 1.0f + expf(-acc[co]));
     for (int co = 0; co < channels; ++co) {
-      const float sig = __fdiv_rn(1.0f, 1.0f + expf(-acc[co]));
+      float sig = acc[co];
+      if (pp.flags & kTtaChannelSym) sig += acc[channels - 1 - co];  // reference-literal --augment
       asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)co * out_vol), "f"(sig * m) : "memory");
     }
   }

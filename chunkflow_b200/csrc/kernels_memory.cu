@@ -1,5 +1,8 @@
 // HBM-bound kernels of the inference hot path (sm_100a).  See kernels_memory.cuh.
 #include "kernels_memory.cuh"
+
+#include <algorithm>
+
 #include "chunkflow_b200.h"
 
 namespace cfb {
@@ -12,6 +15,9 @@ __device__ __forceinline__ float u8_to_unit(unsigned int v) {
   // numpy: x.astype(float32); x /= 255  -> IEEE fp32 division (not a reciprocal multiply)
   return __fdiv_rn((float)v, 255.0f);
 }
+
+// max that propagates NaN (fmaxf drops it)
+__device__ __forceinline__ float nan_max(float a, float b) { return (b > a || b != b) ? b : a; }
 
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
@@ -99,7 +105,11 @@ blend_patches_kernel(const float* __restrict__ net, int cnet, Int3 ip, Int3 op, 
         const float mk = mask ? __ldg(mask + ((int64_t)z * op.y + y) * op.x + x + k) : 1.f;
         const float* sp = net + (int64_t)b * cnet * in_vol + ((int64_t)(z + crop.z) * ip.y + (y + crop.y)) * ip.x + (x + k + crop.x);
         float* dp = out + ((int64_t)gz * os.y + gy) * os.x + gx;
-        for (int c = 0; c < channels; ++c) red_add_f32(dp + (int64_t)c * out_vol, sp[(int64_t)c * in_vol] * scale * mk);
+        for (int c = 0; c < channels; ++c) {
+          float v = sp[(int64_t)c * in_vol];
+          if (pp.flags & kTtaChannelSym) v += sp[(int64_t)(channels - 1 - c) * in_vol];  // + the channel-reversed copy
+          red_add_f32(dp + (int64_t)c * out_vol, v * scale * mk);
+        }
       }
       continue;
     }
@@ -188,14 +198,15 @@ __global__ void __launch_bounds__(kThreads)
 weight_volume_kernel(const float* __restrict__ mask, Int3 op, const int* __restrict__ cover_z,
                      const int* __restrict__ cover_y, const int* __restrict__ cover_x,
                      const int* __restrict__ oz0, const int* __restrict__ oy0, const int* __restrict__ ox0,
-                     Int3 os, float* __restrict__ w, bool invert) {
-  const int64_t total = (int64_t)os.z * os.y * os.x;
+                     Int3 os, float* __restrict__ w, bool invert, int z_begin, int nz) {
+  // planes [z_begin, z_begin + nz) of the volume; w holds those planes only
+  const int64_t total = (int64_t)nz * os.y * os.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int x = (int)(i % os.x);
     int64_t r = i / os.x;
     int y = (int)(r % os.y);
-    int z = (int)(r / os.y);
+    int z = z_begin + (int)(r / os.y);
     float acc = 0.0f;  // patch-list order: z-major, then y, then x -> same fp32 sum as numpy's +=
     for (int a = 0; a < kMaxCover; ++a) {
       int pz = cover_z[z * kMaxCover + a];
@@ -240,7 +251,7 @@ normalize_kernel(float* __restrict__ out, const float* __restrict__ w, bool w_is
         float4 v = *p;
         v.x *= s.x; v.y *= s.y; v.z *= s.z; v.w *= s.w;
         if (force_zero) v = make_float4(0.f, 0.f, 0.f, 0.f);
-        vmax = fmaxf(vmax, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        vmax = nan_max(nan_max(vmax, nan_max(v.x, v.y)), nan_max(v.z, v.w));
         __stcs(p, v);
       }
     }
@@ -252,14 +263,16 @@ normalize_kernel(float* __restrict__ out, const float* __restrict__ w, bool w_is
       for (int c = 0; c < channels; ++c) {
         float v = out[(int64_t)c * cstride + i] * s;
         if (force_zero) v = 0.f;
-        vmax = fmaxf(vmax, v);
+        vmax = nan_max(vmax, v);
         out[(int64_t)c * cstride + i] = v;
       }
     }
   }
-  // NaN must not slip through the range check: fmaxf drops NaN, so test explicitly
-  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  if ((threadIdx.x & 31) == 0 && max_bits != nullptr && vmax > 0.f) atomicMax(max_bits, __float_as_uint(vmax));
+  // NaN must not slip through the range check (the reference's assert_array_less raises on NaN): nan_max keeps it,
+  // and a quiet-NaN bit pattern (0x7fc00000) is larger than the bits of every finite positive float
+  for (int o = 16; o > 0; o >>= 1) vmax = nan_max(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if ((threadIdx.x & 31) == 0 && max_bits != nullptr && !(vmax <= 0.f))
+    atomicMax(max_bits, vmax != vmax ? 0x7fc00000u : __float_as_uint(vmax));
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -330,9 +343,37 @@ void launch_crop_mask(const float* net, int cnet, Int3 ip, Int3 op, Int3 crop, c
 
 void launch_weight_volume(const float* mask, Int3 op, const int* cover_z, const int* cover_y, const int* cover_x,
                           const int* oz0, const int* oy0, const int* ox0, Int3 os, float* w, bool invert,
-                          cudaStream_t s) {
-  weight_volume_kernel<<<grid_for(vol(os)), kThreads, 0, s>>>(mask, op, cover_z, cover_y, cover_x, oz0, oy0, ox0,
-                                                              os, w, invert);
+                          cudaStream_t s, int z_begin, int z_end) {
+  if (z_end < 0) z_end = os.z;
+  const int nz = z_end - z_begin;
+  if (nz <= 0) return;
+  weight_volume_kernel<<<grid_for((int64_t)nz * os.y * os.x), kThreads, 0, s>>>(mask, op, cover_z, cover_y, cover_x, oz0, oy0, ox0,
+                                                                               os, w, invert, z_begin, nz);
+  CFB_LAUNCH_CHECK();
+}
+
+// dst += src (halo planes received from another rank, BASELINE config #5)
+__global__ void __launch_bounds__(256) halo_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  const int64_t nq = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+  if (vec) {
+    for (int64_t i = tid; i < nq; i += step) {
+      float4 a = reinterpret_cast<float4*>(dst)[i];
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      reinterpret_cast<float4*>(dst)[i] = a;
+    }
+    for (int64_t i = (nq << 2) + tid; i < n; i += step) dst[i] += src[i];
+  } else {
+    for (int64_t i = tid; i < n; i += step) dst[i] += src[i];
+  }
+}
+
+void launch_halo_add(float* dst, const float* src, int64_t n, cudaStream_t s) {
+  if (n <= 0) return;
+  int64_t blocks = std::min<int64_t>(ceil_div64(n / 4 + 1, 256), 148 * 16);
+  halo_add_kernel<<<(int)blocks, 256, 0, s>>>(dst, src, n);
   CFB_LAUNCH_CHECK();
 }
 

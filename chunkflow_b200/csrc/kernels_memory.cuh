@@ -33,7 +33,10 @@ void launch_crop_mask(const float* net, int cnet, Int3 in_patch, Int3 out_patch,
 // order) of mask(v - o_p); writes 1/W if `invert`, else W.
 void launch_weight_volume(const float* mask, Int3 out_patch, const int* cover_z, const int* cover_y,
                           const int* cover_x, const int* ostart_z, const int* ostart_y, const int* ostart_x,
-                          Int3 out_size, float* w, bool invert, cudaStream_t s);
+                          Int3 out_size, float* w, bool invert, cudaStream_t s, int z_begin = 0, int z_end = -1);
+
+// dst[i] += src[i]: halo planes received from another rank (one chunk split over GPUs, BASELINE config #5).
+void launch_halo_add(float* dst, const float* src, int64_t n, cudaStream_t s);
 
 // a12+a13 (reference inferencer.py:460-466): out *= winv (broadcast over channels), and
 // track the maximum into *max_bits (float bits, values are >= 0).  If *zero_flag == 0

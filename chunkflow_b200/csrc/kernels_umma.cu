@@ -231,18 +231,36 @@ __device__ __forceinline__ void head_blend_16(const float (&v)[16], const FusedT
       a1 = fmaf(v[k], s_head[16 + k], a1);
       a2 = fmaf(v[k], s_head[32 + k], a2);
     }
-    const float s0 = __fdividef(m, 1.0f + __expf(-a0)), s1 = __fdividef(m, 1.0f + __expf(-a1)), s2 = __fdividef(m, 1.0f + __expf(-a2));
+    float s0 = __fdividef(m, 1.0f + __expf(-a0)), s1 = __fdividef(m, 1.0f + __expf(-a1)), s2 = __fdividef(m, 1.0f + __expf(-a2));
+    if (pp.flags & kTtaChannelSym) {  // reference-literal --augment: the variant plus its channel-reversed copy
+      const float e = s0 + s2;
+      s0 = e; s2 = e; s1 += s1;
+    }
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst), "f"(s0) : "memory");
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + out_vol), "f"(s1) : "memory");
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + 2 * out_vol), "f"(s2) : "memory");
     return;
   }
-  for (int co = 0; co < t.channels; ++co) {
-    float acc = s_head[t.channels * 16 + co];
+  float sig[8];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc = fmaf(v[k], s_head[co * 16 + k], acc);
-    const float sig = __fdiv_rn(1.0f, 1.0f + expf(-acc));
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)co * out_vol), "f"(sig * m) : "memory");
+  for (int co = 0; co < 8; ++co) {
+    if (co < t.channels) {
+      float acc = s_head[t.channels * 16 + co];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(v[k], s_head[co * 16 + k], acc);
+      sig[co] = __fdiv_rn(1.0f, 1.0f + expf(-acc));
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < 8; ++co) {
+    if (co < t.channels) {
+      float o = sig[co];
+      if (pp.flags & kTtaChannelSym) {
+#pragma unroll
+        for (int c2 = 0; c2 < 8; ++c2) if (c2 == t.channels - 1 - co) o += sig[c2];
+      }
+      asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)co * out_vol), "f"(o * m) : "memory");
+    }
   }
 }
 

@@ -50,7 +50,7 @@ class Inferencer(object):
                  input_size: Union[tuple, list, Cartesian] = None,
                  mask_output_chunk: bool = True,
                  mask_myelin_threshold=None,
-                 augment: bool = False,
+                 augment: Union[bool, str] = False,
                  dry_run: bool = False,
                  device: int = None,
                  precision=None):
@@ -126,11 +126,17 @@ class Inferencer(object):
         if isinstance(convnet_weight_path, str):
             convnet_weight_path = os.path.expanduser(convnet_weight_path)
 
-        self.transform_sequences = TransformSequences() if augment else None
+        # augment: False | True (= 'reference': the reference's arithmetic, literally -- its flips act on the channel /
+        # batch axes, transform.py:30-52) | 'spatial' (the intended spatial flips; explicit opt-in, different numbers)
+        self.augment = _native.augment_code(augment)
+        self.transform_sequences = None
+        if self.augment:
+            self.transform_sequences = TransformSequences(
+                'spatial' if self.augment == _native.AUGMENT_SPATIAL else 'reference')
         self._prepare_patch_inferencer(framework, convnet_model, convnet_weight_path, bump, precision)
 
     # ------------------------------------------------------------------------------------
-    def _engine(self, framework_code, precision=None, augment=False):
+    def _engine(self, framework_code, precision=None, augment=0):
         return _native.Engine(
             input_patch_size=self.input_patch_size,
             # a host plugin returns cropped patches: to the device they are crop-free patches
@@ -167,9 +173,9 @@ class Inferencer(object):
                 "(chunkflow_b200/convnet/unet3l.py) only; arbitrary torch models have no CPU/eager fallback here. "
                 "Wrap other backends as a `universal` plugin.")
         if framework in ('b200', 'pytorch'):
-            # --augment: the 8 flip/transpose variants of every patch run as 8 batch entries on the device and
-            # are averaged by the blend (spatial flips, see transform.py for the deviation from the reference)
-            self.engine = self._engine(_native.FRAMEWORK_UNET3L, precision, augment=self.transform_sequences is not None)
+            # --augment on the device: the variants of a patch are extra batch entries, averaged by the blend
+            # (reference-literal by default, 'spatial' on request; include/chunkflow_b200.h CFB_AUGMENT_*)
+            self.engine = self._engine(_native.FRAMEWORK_UNET3L, precision, augment=self.augment)
             self.engine.load_state_dict(b200_patch.load_state_dict(convnet_model, convnet_weight_path))
         elif framework == 'identity':
             if self.transform_sequences is not None:
@@ -193,6 +199,11 @@ class Inferencer(object):
         else:
             raise Exception(f'invalid inference backend: {framework}')
         self.input_patch_buffer = None
+        if self.patch_inferencer is not None and self.transform_sequences is not None:
+            # the transposed patch is fed to the same backend: it must have the same shape (the reference fails
+            # inside numpy / the backend here)
+            if self.input_patch_size[1] != self.input_patch_size[2] or self.output_patch_size[1] != self.output_patch_size[2]:
+                raise ValueError('--augment transposes y and x: the patch must be square in y, x')
         if self.patch_inferencer is not None:
             # reused host staging buffer, like the reference (inferencer.py:154-155)
             self.input_patch_buffer = np.zeros(

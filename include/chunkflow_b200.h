@@ -52,6 +52,17 @@ extern "C" {
 #define CFB_PRECISION_F16X3_UMMA 1 /* tcgen05 fp16 hi/lo split, fp32 accumulate (~fp32 accuracy) */
 #define CFB_PRECISION_F16_UMMA 2   /* tcgen05 single-pass fp16, fp32 accumulate (reference --dtype float16) */
 
+/* test-time augmentation (`--augment`, reference inferencer.py:422-431 + transform.py).
+ * REFERENCE reproduces the reference's arithmetic literally: its FlipLR / FlipUD call np.fliplr / np.flipud on
+ * arr[..., z, :, :] of the 5-D (B, C, z, y, x) buffers, i.e. they reverse the CHANNEL and BATCH axes
+ * (transform.py:30-52), so the average over its 8 sequences is
+ *   1/4 * (n(x) + rev_c n(x) + T n(T x) + rev_c T n(T x)),   T = transpose y<->x, rev_c = output channels reversed.
+ * SPATIAL is the evidently intended augmentation: the 8 combinations of {transpose} x {flip x} x {flip y}, each
+ * undone on the output, averaged (an explicit opt-in; it does NOT reproduce the reference's numbers). */
+#define CFB_AUGMENT_NONE 0
+#define CFB_AUGMENT_REFERENCE 1
+#define CFB_AUGMENT_SPATIAL 2
+
 /* dtype of the input chunk */
 #define CFB_DTYPE_U8 0
 #define CFB_DTYPE_F32 1
@@ -71,7 +82,7 @@ typedef struct cfb_params {
   int32_t num_output_channels;     /* channels returned (network may produce more; first N kept) */
   int32_t batch_size;              /* patches in flight per launch (scheduling hint) */
   int32_t mask_output_chunk;       /* 1: normalise by the accumulated weight volume */
-  int32_t augment;                 /* 1: 8-fold test-time augmentation (reference transform.py) */
+  int32_t augment;                 /* CFB_AUGMENT_*: test-time augmentation (reference transform.py:114-156) */
   int32_t has_myelin_threshold;    /* 1: drop last channel, zero where it is >= threshold */
   float mask_myelin_threshold;
   int32_t check_output_range;      /* 1: fail with CFB_ERR_OUTPUT_RANGE like the reference assert */
@@ -122,17 +133,31 @@ int cfb_infer_chunk_device(cfb_handle h, const void* d_in, int32_t in_dtype,
 int cfb_infer_chunk_host(cfb_handle h, const void* h_in, int32_t in_dtype,
                          int64_t cz, int64_t cy, int64_t cx, float* h_out);
 
-/* Slab variant used when one oversized chunk is split across GPUs: processes only the
- * patches whose z-row index is in [zrow_begin, zrow_end) and leaves d_out as the
- * UN-normalised partial sum; d_weight (oz,oy,ox) receives this slab's partial weight
- * sum.  The caller adds the halo rows of neighbouring ranks (NCCL) and then calls
- * cfb_normalize_device. */
+/* One oversized chunk split across GPUs (BASELINE config #5; the reference has no counterpart, its unit of
+ * parallelism is one process per GPU on independent chunks, distributed/kubernetes/deploy.yml:37):
+ *   cfb_infer_slab_device     processes only the patches whose z-row index is in [zrow_begin, zrow_end) and leaves
+ *                             d_out as the UN-normalised partial sum; d_weight (oz,oy,ox), if not NULL, receives this
+ *                             slab's partial weight sum.
+ *   cfb_slab_nonzero          the any-nonzero flag of the input of the last slab / chunk call (all ranks OR it to
+ *                             reproduce the reference's all-zero shortcut, inferencer.py:387-393); synchronises.
+ *   cfb_halo_add_device       d_dst[i] += d_src[i]: the owner of a plane adds the partial sums received from the
+ *                             other ranks whose slabs overlap it (NCCL send/recv of the planes, then this kernel).
+ *   cfb_weight_volume_device  planes [z_begin, z_end) of the weight volume (sum of the bump masks of ALL patches of
+ *                             a (cz,cy,cx) chunk, reference inferencer.py:294-333; 1/W if `invert`): pure geometry,
+ *                             so the owner computes it locally -- no weight halo is exchanged.
+ *   cfb_normalize_device      d_out *= 1/d_weight (or *= d_weight if weight_is_inverse; NULL = no weight), the
+ *                             reference's `< 1.0001` assertion (CFB_ERR_OUTPUT_RANGE, when check_output_range is set),
+ *                             myelin masking; all_zero_input != 0 forces the result to zero. */
 int cfb_infer_slab_device(cfb_handle h, const void* d_in, int32_t in_dtype,
                           int64_t cz, int64_t cy, int64_t cx,
                           int64_t zrow_begin, int64_t zrow_end,
                           float* d_out, float* d_weight, void* stream);
-int cfb_normalize_device(cfb_handle h, float* d_out, const float* d_weight,
-                         int64_t channels, int64_t oz, int64_t oy, int64_t ox, void* stream);
+int cfb_slab_nonzero(cfb_handle h, int32_t* nonzero, void* stream);
+int cfb_halo_add_device(float* d_dst, const float* d_src, int64_t count, void* stream);
+int cfb_weight_volume_device(cfb_handle h, int64_t cz, int64_t cy, int64_t cx, int64_t z_begin, int64_t z_end,
+                             int32_t invert, float* d_weight, void* stream);
+int cfb_normalize_device(cfb_handle h, float* d_out, const float* d_weight, int32_t weight_is_inverse,
+                         int64_t channels, int64_t oz, int64_t oy, int64_t ox, int32_t all_zero_input, void* stream);
 
 /* PatchInferencer plugin level: `batch` input patches (batch,1,pz,py,px) float32 in
  * [0,1] on the host -> (batch,C,oz,oy,ox) float32 on the host, already cropped and

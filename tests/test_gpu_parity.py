@@ -1,5 +1,7 @@
 """Parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle,
 the golden vectors of the real reference, and size-independent properties."""
+import os
+
 import numpy as np
 import pytest
 
@@ -339,22 +341,141 @@ def test_slab_entry_point_matches_whole_chunk():
     np.testing.assert_allclose(d_acc.cpu().numpy(), whole, rtol=0, atol=BLEND_ATOL)
 
 
-@pytest.mark.parametrize("precision", ["f16x3", "simt"])
-def test_device_test_time_augmentation(unet_model, precision):
-    """--augment on the device network path: 8 spatial flip/transpose variants per patch, averaged.
-    Checked against the oracle's `spatial` augmentation (the product's documented deviation from the
-    reference's channel/batch-axis flips)."""
+@pytest.mark.parametrize("precision", [None, "simt"])
+@pytest.mark.parametrize("augment", [True, "spatial"])
+def test_device_test_time_augmentation(unet_model, precision, augment):
+    """--augment on the device network path.  `augment=True` reproduces the REFERENCE's arithmetic (its FlipLR / FlipUD
+    act on the channel / batch axes, transform.py:30-52: two network evaluations, each blended with its channel-reversed
+    copy) and is checked against the oracle's literal mode, which tests/test_oracle_vs_reference.py pins to the real
+    reference; `augment='spatial'` is the explicit opt-in with 8 spatial variants."""
     rng = np.random.default_rng(29)
     img = rng.integers(0, 256, size=(10, 40, 44), dtype=np.uint8)
     kw = dict(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3)
-    inf = _inferencer(model=MODEL_FILE, framework="b200", batch_size=8, augment=True, precision=precision, **kw)
+    inf = _inferencer(model=MODEL_FILE, framework="b200", batch_size=8, augment=augment, precision=precision, **kw)
     out = inf(Chunk(img))
-    o, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, augment="spatial", **kw)
+    o, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, augment=augment, **kw)
     plain, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, **kw)
     err = np.abs(out.array - o).max()
-    print("device TTA max-abs", precision, err, "| TTA changes the result by", np.abs(o - plain).max())
-    assert err <= (NET_ATOL_F32 if precision == "f16x3" else NET_ATOL_SIMT)
+    print("device TTA max-abs", augment, precision, err, "| TTA changes the result by", np.abs(o - plain).max())
+    assert err <= (NET_ATOL_F32 if precision is None else NET_ATOL_SIMT)
     assert np.abs(o - plain).max() > 1e-2   # the augmentation is not a no-op for a real network
+    if augment is True:   # the reference's average is symmetric under channel reversal
+        np.testing.assert_allclose(out.array[0], out.array[2], rtol=0, atol=1e-6)
+
+
+def test_host_plugin_test_time_augmentation_reference_literal(unet_model):
+    """--augment around a host patch plug-in (framework='prebuilt'): transform.py in its reference-literal mode."""
+    from chunkflow_b200.flow.divid_conquer.patch.b200 import B200
+    rng = np.random.default_rng(37)
+    img = rng.integers(0, 256, size=(10, 40, 44), dtype=np.uint8)
+    kw = dict(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3)
+    pi = B200(MODEL_FILE, None, (8, 32, 32), (8, 32, 32), (2, 8, 8), num_output_channels=3, batch_size=1)
+    out = _inferencer(model=pi, framework="prebuilt", batch_size=1, augment=True, **kw)(Chunk(img))
+    o, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, augment=True, **kw)
+    assert np.abs(out.array - o).max() <= NET_ATOL_F32
+
+
+# ---- parity at the BENCHMARKED geometry (BASELINE configs #2 / #3: the tilings, the batch of 12 patches in flight and the
+# ---- cross-patch fp32 reductions the headline number runs with) ------------------------------------------------------
+def _oracle_threads():
+    import torch
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or 1
+    except Exception:
+        n = max(1, (os.cpu_count() or 2) // 2)
+    n = min(n, len(os.sched_getaffinity(0)))
+    torch.set_num_threads(max(1, n))
+
+
+def _bench_geometry_case(unet_model, chunk_shape, patch, overlap, batch, seed):
+    _oracle_threads()
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=chunk_shape, dtype=np.uint8)
+    inf = _inferencer(model=MODEL_FILE, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
+                      batch_size=batch, framework="b200", mask_output_chunk=True)
+    out = inf(Chunk(img)).array
+    o, _ = O.infer_chunk(img, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
+                         framework="pytorch", model=unet_model)
+    err = float(np.abs(out - o).max())
+    print("bench-geometry parity", chunk_shape, patch, "patches", len(inf.patch_slices_list), "batch", batch, "max-abs", err)
+    assert out.shape == o.shape and err <= NET_ATOL_F32
+    again = inf(Chunk(img)).array    # cached tables, autotuned tilings: same result up to the order of the fp32 reductions
+    assert np.abs(again - out).max() <= 1e-5
+
+
+def test_bench_geometry_config3_batch12(unet_model):
+    """Patch 32x256x256, overlap 8x64x64, exactly 12 patches = one full batch of the benchmark configuration (#3)."""
+    _bench_geometry_case(unet_model, (80, 448, 448), (32, 256, 256), (8, 64, 64), 12, 101)
+
+
+def test_bench_geometry_config3_clamped_chunk(unet_model):
+    """Same patch geometry on a chunk whose last patch per axis is clamped back (heavily overlapping patches in flight)."""
+    _bench_geometry_case(unet_model, (40, 300, 260), (32, 256, 256), (8, 64, 64), 12, 102)
+
+
+@pytest.mark.slow
+def test_bench_geometry_config2_crop_128x512x512(unet_model):
+    """BASELINE config #2's geometry (patch 20x256x256, overlap 4x64x64, batch 12) on a 128x512x512 crop: 72 patches
+    (SURVEY section 8d asks for full-volume parity on 'a <=128x512x512 crop-config of #2')."""
+    _bench_geometry_case(unet_model, (128, 512, 512), (20, 256, 256), (4, 64, 64), 12, 103)
+
+
+def test_nan_and_overflow_trip_the_range_check():
+    """The reference's `assert np.all(out < 1.0001)` (inferencer.py:465-466) raises on NaN too; so must the device check."""
+    ident = _inferencer(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=1, batch_size=3,
+                        framework="identity")
+    bad = np.full((10, 40, 40), 0.5, np.float32)
+    bad[3, 7, 9] = np.nan
+    with pytest.raises(AssertionError):
+        ident(Chunk(bad))
+    bad[3, 7, 9] = np.inf
+    with pytest.raises(AssertionError):
+        ident(Chunk(bad))
+    bad[3, 7, 9] = 0.5
+    assert np.isfinite(ident(Chunk(bad)).array).all()
+    # a NaN weight makes every network output NaN
+    from chunkflow_b200.flow.divid_conquer.patch import b200 as b200_patch
+    inf = _inferencer(model=MODEL_FILE, input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3,
+                      batch_size=2, framework="b200")
+    state = dict(b200_patch.load_state_dict(MODEL_FILE, None))
+    w = np.array(state["dec0.2.weight"], dtype=np.float32, copy=True)
+    w.flat[5] = np.nan
+    state["dec0.2.weight"] = w
+    inf.engine.load_state_dict(state)
+    with pytest.raises(AssertionError):
+        inf(Chunk.create(size=(8, 32, 32)))
+
+
+def test_host_plugin_shape_errors_and_myelin_zero_threshold():
+    """a plug-in that returns a wrongly shaped array must raise (the native side would read out of bounds);
+    mask_myelin_threshold=0.0 means 'off', as in the reference (truthiness, inferencer.py:468)."""
+    class Uncropped:
+        compute_device = "host"
+        def __call__(self, patch):   # forgets to crop to the output patch
+            return np.repeat(patch, 2, axis=1)
+    kw = dict(input_patch_size=(10, 40, 40), output_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8))
+    inf = _inferencer(model=Uncropped(), num_output_channels=2, framework="prebuilt", batch_size=2, **kw)
+    with pytest.raises(ValueError):
+        inf(Chunk.create(size=(16, 64, 64)))
+
+    class TooFewChannels:
+        compute_device = "host"
+        def __call__(self, patch):
+            return patch[:, :, 1:-1, 4:-4, 4:-4]
+    inf = _inferencer(model=TooFewChannels(), num_output_channels=2, framework="prebuilt", batch_size=2, **kw)
+    with pytest.raises(ValueError):
+        inf(Chunk.create(size=(16, 64, 64)))
+    with pytest.raises(ValueError):   # non-square patch with --augment around a host plug-in
+        _inferencer(model=TooFewChannels(), input_patch_size=(8, 32, 40), output_patch_overlap=(2, 8, 8), num_output_channels=1,
+                    framework="prebuilt", augment=True)
+    rng = np.random.default_rng(5)
+    img = rng.random((10, 40, 40)).astype(np.float32)
+    my = _inferencer(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=4, framework="identity",
+                     mask_myelin_threshold=0.0, batch_size=3)
+    res = my(Chunk(img))
+    assert res.shape == (4, 10, 40, 40)
+    np.testing.assert_allclose(res.array[0], img, atol=BLEND_ATOL)
 
 
 def test_kernel_variants_agree(monkeypatch, unet_model):

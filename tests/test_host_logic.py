@@ -86,15 +86,27 @@ def test_patch_mask_partition_of_unity():
     np.testing.assert_allclose(centre, 1.0, atol=1e-6)
 
 
-def test_product_tta_matches_oracle_for_spatial_transposes():
+def test_product_tta_modes_match_the_oracle():
+    """Host plug-in augmentation: 'reference' (default) is the reference's literal arithmetic -- flips on the channel /
+    batch axes, inverse steps in forward order (transform.py:30-52,147-156), pinned to the real reference through the
+    oracle in tests/test_oracle_vs_reference.py; 'spatial' is the explicit opt-in."""
     from chunkflow_b200.flow.divid_conquer.transform import TransformSequences
+    from oracle import inferencer_oracle as O
     rng = np.random.default_rng(3)
-    a = rng.random((1, 1, 3, 8, 8)).astype(np.float32)
-    ts = TransformSequences()
-    fw = ts.forward(a)
-    assert len(fw) == 8 and all(np.array_equal(x, y) for x, y in zip(ts.backward(fw), [a] * 8))
-    # distinct spatial variants (the reference's flips act on batch/channel axes instead)
-    assert len({x.tobytes() for x in fw}) == 8
+    a = rng.random((2, 3, 3, 8, 8)).astype(np.float32)
+    lit = TransformSequences()
+    assert lit.mode == "reference"
+    fw = lit.forward(a)
+    assert len(fw) == 8 and all(np.array_equal(x, y) for x, y in zip(fw, O.tta_forward(a)))
+    assert all(np.array_equal(x, y) for x, y in zip(lit.backward(fw), O.tta_backward(O.tta_forward(a))))
+    assert all(np.array_equal(x, a) for x in lit.backward(fw))
+    sp = TransformSequences("spatial")
+    fw = sp.forward(a)
+    assert len({x.tobytes() for x in fw}) == 8 and all(np.array_equal(x, a) for x in sp.backward(fw))
+    with pytest.raises(ValueError):
+        TransformSequences("rotate")
+    assert _native.augment_code(True) == _native.AUGMENT_REFERENCE and _native.augment_code("spatial") == _native.AUGMENT_SPATIAL
+    assert _native.augment_code(False) == _native.AUGMENT_NONE
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")

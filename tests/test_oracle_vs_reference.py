@@ -78,3 +78,32 @@ def test_myelin_and_patch_mask(ref):
     _, _, PatchMask = ref
     for ps, ov in [((10, 128, 128), (2, 32, 32)), ((8, 32, 32), (2, 8, 8))]:
         assert np.array_equal(np.asarray(PatchMask(ps, ov)), O.make_patch_mask(ps, ov))
+
+
+def test_cropped_output_patch_and_crop_margin(ref):
+    """output patch smaller than the input patch, explicit crop margin through `patch_num`, a global
+    voxel offset, no chunk-wise mask.  (The reference's own test of this configuration is skipped upstream as 'known bug',
+    test_inferencer.py:98-139; with mask_output_chunk=True the reference itself produces NaN / asserts.)  The GPU path is
+    compared with the oracle on exactly this configuration in tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(13)
+    img = rng.integers(1, 256, size=(2 * 6 + 4, 2 * 24 + 16, 2 * 24 + 16), dtype=np.uint8)
+    kw = dict(input_patch_size=(10, 40, 40), output_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8))
+    r = _run_ref(ref, img, offset=(123, 345, 567), num_output_channels=1, framework="identity", batch_size=5,
+                 mask_output_chunk=False, patch_num=(2, 2, 2), **kw)
+    o, off = O.infer_chunk(img, (123, 345, 567), num_output_channels=1, framework="identity", mask_output_chunk=False, **kw)
+    assert tuple(r.voxel_offset) == off and r.shape == o.shape
+    assert np.array_equal(r.array, o)
+
+
+def test_network_test_time_augmentation_literal(ref, unet_model):
+    """--augment with a REAL network through the reference: its flips act on the channel / batch axes (transform.py:30-52);
+    the oracle's literal mode (what the device path is tested against) reproduces the reference bit for bit."""
+    from conftest import MODEL_FILE
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, size=(10, 36, 36), dtype=np.uint8)
+    kw = dict(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3)
+    r = _run_ref(ref, img, model=MODEL_FILE, batch_size=1, framework="pytorch", mask_output_chunk=True, augment=True, **kw)
+    o, _ = O.infer_chunk(img, framework="pytorch", model=unet_model, augment=True, **kw)
+    np.testing.assert_allclose(r.array, o, rtol=0, atol=1e-7)
+    # ... and equals 1/4 (n(x) + rev_c n(x) + T n(T x) + rev_c T n(T x)): symmetric under channel reversal
+    np.testing.assert_allclose(o[0], o[2], rtol=0, atol=1e-6)   # up to the order of the 8-term fp32 sum

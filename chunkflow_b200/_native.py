@@ -15,7 +15,7 @@ import numpy as np
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 FRAMEWORK_UNET3L, FRAMEWORK_IDENTITY = 0, 1
-PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA = 0, 1, 2
+PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA, PRECISION_F16F8_UMMA = 0, 1, 2, 3
 DTYPE_U8, DTYPE_F32 = 0, 1
 AUGMENT_NONE, AUGMENT_REFERENCE, AUGMENT_SPATIAL = 0, 1, 2
 QUANTIZE_XY, QUANTIZE_Z = 0, 1

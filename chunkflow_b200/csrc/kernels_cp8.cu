@@ -3,6 +3,7 @@
 // transposed convolution and the 1x1x1 head.  See kernels_umma.cuh.
 #include "kernels_umma.cuh"
 
+#include "act_format.cuh"
 #include "chunkflow_b200.h"
 
 namespace cfb {
@@ -29,23 +30,50 @@ __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
   float2 a = unpack2(r.x), b = unpack2(r.y), c = unpack2(r.z), d = unpack2(r.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
-// load the 8 channels of chunk `plane0/parts` at voxel `vox` as fp32 (hi + lo)
-__device__ __forceinline__ void load8(const uint4* __restrict__ base, size_t plane0, int parts, size_t pvol, size_t vox,
+// Every kernel below takes the activation number format `fmt` (ActFmt: 1 = fp16, 2 = fp16 hi + lo, 3 = f16f8, see
+// act_format.cuh) and addresses an 8-channel chunk by the index of its first plane, chunk * fmt_planes(fmt).
+// load the 8 channels of the chunk whose first plane is `plane0` at voxel `vox` as fp32
+__device__ __forceinline__ void load8(const uint4* __restrict__ base, size_t plane0, int fmt, size_t pvol, size_t vox,
                                       float (&v)[8]) {
+  if (fmt == kFmtF16F8) {
+    // H record of this chunk + its half of the L8 record of the K step (plane (chunk | 1, part 1))
+    const uint4 h = __ldg(base + plane0 * pvol + vox);
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(base + ((plane0 | 2) + 1) * pvol + vox) + ((plane0 >> 1) & 1));
+    af_decode8(h, l.x, l.y, v);
+    return;
+  }
   unpack8(__ldg(base + plane0 * pvol + vox), v);
-  if (parts == 2) {
+  if (fmt == kFmtF16x2) {
     float l[8];
     unpack8(__ldg(base + (plane0 + 1) * pvol + vox), l);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += l[i];
   }
 }
-__device__ __forceinline__ void store8(uint4* __restrict__ base, size_t plane0, int parts, size_t pvol, size_t vox,
+__device__ __forceinline__ void store8(uint4* __restrict__ base, size_t plane0, int fmt, size_t pvol, size_t vox,
                                        const float (&v)[8]) {
+  if (fmt == kFmtF16F8) {
+    float s[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s[i] = fminf(fmaxf(v[i] * kActAlpha, -kHalfMax), kHalfMax);
+      const float h = __half2float(__float2half_rn(s[i]));
+      l[i] = (s[i] - h) * kActLambda;
+      s[i] = h;
+    }
+    base[plane0 * pvol + vox] = make_uint4(pack2(s[0], s[1]), pack2(s[2], s[3]), pack2(s[4], s[5]), pack2(s[6], s[7]));
+    const int half = (int)((plane0 >> 1) & 1);  // which 8 of the 16 channels of the K step
+    reinterpret_cast<uint2*>(base + ((plane0 & ~(size_t)2) + 1) * pvol + vox)[half] =
+        make_uint2(af_pack_e4m3x4(v[0] * kActGamma, v[1] * kActGamma, v[2] * kActGamma, v[3] * kActGamma),
+                   af_pack_e4m3x4(v[4] * kActGamma, v[5] * kActGamma, v[6] * kActGamma, v[7] * kActGamma));
+    reinterpret_cast<uint2*>(base + ((plane0 | 2) + 1) * pvol + vox)[half] =
+        make_uint2(af_pack_e4m3x4(l[0], l[1], l[2], l[3]), af_pack_e4m3x4(l[4], l[5], l[6], l[7]));
+    return;
+  }
   uint4 hi, lo;
   split8(v, hi, lo);
   base[plane0 * pvol + vox] = hi;
-  if (parts == 2) base[(plane0 + 1) * pvol + vox] = lo;
+  if (fmt == kFmtF16x2) base[(plane0 + 1) * pvol + vox] = lo;
 }
 
 __global__ void __launch_bounds__(kT)
@@ -59,7 +87,7 @@ planar_to_cp8_kernel(const float* __restrict__ in, uint4* __restrict__ out, int 
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = in[((b * channels) + chunk * 8 + e) * pvol + vox];
-    store8(out, bc * parts, parts, pvol, vox, v);
+    store8(out, bc * fmt_planes(parts), parts, pvol, vox, v);
   }
 }
 
@@ -72,7 +100,7 @@ cp8_to_planar_kernel(const uint4* __restrict__ in, float* __restrict__ out, int 
     const size_t bc = i / pvol;
     const size_t b = bc / chunks, chunk = bc % chunks;
     float v[8];
-    load8(in, bc * parts, parts, pvol, vox, v);
+    load8(in, bc * fmt_planes(parts), parts, pvol, vox, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) out[((b * channels) + chunk * 8 + e) * pvol + vox] = v[e];
   }
@@ -139,8 +167,8 @@ first_conv_cp8_kernel(const void* __restrict__ src, Int3 cs, const PatchPos* __r
   for (int h = 0; h < 2; ++h) {
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(acc[h * 8 + i] + s_b[h * 8 + i], 0.f);
-    store8(out, ((size_t)b * 2 + h) * parts, parts, pvol, vox, v);
+    for (int i = 0; i < 8; ++i) { const float t = acc[h * 8 + i] + s_b[h * 8 + i]; v[i] = t < 0.f ? 0.f : t; }  // NaN passes, like torch.relu
+    store8(out, ((size_t)b * 2 + h) * fmt_planes(parts), parts, pvol, vox, v);
   }
 }
 
@@ -186,8 +214,8 @@ first_conv_cp8_const_kernel(const void* __restrict__ src, Int3 cs, const PatchPo
   for (int h = 0; h < 2; ++h) {
     float v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(acc[h * 8 + i] + W.b[h * 8 + i], 0.f);
-    store8(out, ((size_t)b * 2 + h) * parts, parts, pvol, vox, v);
+    for (int i = 0; i < 8; ++i) { const float t = acc[h * 8 + i] + W.b[h * 8 + i]; v[i] = t < 0.f ? 0.f : t; }  // NaN passes, like torch.relu
+    store8(out, ((size_t)b * 2 + h) * fmt_planes(parts), parts, pvol, vox, v);
   }
 }
 
@@ -207,11 +235,11 @@ maxpool_cp8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int pa
     for (int k = 0; k < 4; ++k) {
       const size_t iv = ((size_t)z * isz.y + 2 * y + (k >> 1)) * isz.x + 2 * x + (k & 1);
       float v[8];
-      load8(in, bc * parts, parts, ipvol, iv, v);
+      load8(in, bc * fmt_planes(parts), parts, ipvol, iv, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
     }
-    store8(out, bc * parts, parts, opvol, ov, m);
+    store8(out, bc * fmt_planes(parts), parts, opvol, ov, m);
   }
 }
 
@@ -241,7 +269,7 @@ convT_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w, cons
     for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
     for (int ch = 0; ch < ichunks; ++ch) {
       float v[8];
-      load8(in, ((size_t)b * ichunks + ch) * parts, parts, ipvol, iv, v);
+      load8(in, ((size_t)b * ichunks + ch) * fmt_planes(parts), parts, ipvol, iv, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float* wp = &s_wt[((ch * 8 + e) * 4 + tap) * COUT];
@@ -254,7 +282,7 @@ convT_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w, cons
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = acc[oc * 8 + e] + __ldg(bias + oc * 8 + e);
-      store8(out, ((size_t)b * (COUT / 8) + oc) * parts, parts, opvol, ov, v);
+      store8(out, ((size_t)b * (COUT / 8) + oc) * fmt_planes(parts), parts, opvol, ov, v);
     }
   }
 }
@@ -275,7 +303,7 @@ head_sigmoid_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ 
     for (int co = 0; co < cout; ++co) acc[co] = s_hw[cout * cin + co];
     for (int ch = 0; ch < chunks; ++ch) {
       float v[8];
-      load8(in, (b * chunks + ch) * parts, parts, pvol, vox, v);
+      load8(in, (b * chunks + ch) * fmt_planes(parts), parts, pvol, vox, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         for (int co = 0; co < cout; ++co) acc[co] = fmaf(v[e], s_hw[co * cin + ch * 8 + e], acc[co]);
@@ -313,7 +341,7 @@ head_blend_cp8_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
     for (int co = 0; co < channels; ++co) acc[co] = s_hw[channels * cin + co];
     for (int ch = 0; ch < chunks; ++ch) {
       float v[8];
-      load8(in, ((size_t)b * chunks + ch) * parts, parts, ipvol, iv, v);
+      load8(in, ((size_t)b * chunks + ch) * fmt_planes(parts), parts, ipvol, iv, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         for (int co = 0; co < channels; ++co) acc[co] = fmaf(v[e], s_hw[co * cin + ch * 8 + e], acc[co]);

@@ -81,7 +81,7 @@ conv3_f32_kernel(const float* __restrict__ in0, int c0, const float* __restrict_
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       r[k] = acc[co][k] + bv;
-      if (relu) r[k] = fmaxf(r[k], 0.f);
+      if (relu) r[k] = r[k] < 0.f ? 0.f : r[k];  // NaN passes, like torch.relu
     }
     float* dst = out + ((int64_t)b * cout + co_base + co) * volume + (int64_t)z * plane + (int64_t)y * sz.x + x;
     if (x + 4 <= sz.x && (sz.x & 3) == 0) {

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "act_format.cuh"
 #include "chunkflow_b200.h"
 
 namespace cfb {
@@ -158,6 +159,29 @@ __device__ __forceinline__ void tc_mma_f16_ta(uint32_t d_tmem, uint32_t a_tmem, 
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp8 (e4m3 x e4m3, K = 32) products into the same fp32 accumulators: the correction terms of the f16f8 mode (act_format.cuh)
+__device__ __forceinline__ void tc_mma_f8_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, no-swizzle shared memory matrix descriptor (cute::UMMA::SmemDescriptor), 64 bits:
@@ -168,6 +192,9 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+
+// ReLU that lets NaN through like torch.relu (fmaxf(NaN, 0) would return 0 and hide a broken weight from the range check)
+__device__ __forceinline__ float relu_nan(float v) { return v < 0.f ? 0.f : v; }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -208,6 +235,19 @@ __device__ __forceinline__ void store_cp8_16(const float (&v)[16], int cb, int b
                                                         pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
     }
   }
+}
+
+// f16f8 format: 16 channels (one K step) of a voxel -> H 0..7, H 8..15, A8 0..15, L8 0..15 records
+template <int COUT>
+__device__ __forceinline__ void store_cp8_16_f8(const float (&v)[16], int cb, int b, size_t vox, size_t plane_vox,
+                                                uint4* __restrict__ out16) {
+  uint4 h0, h1, a8, l8;
+  af_encode16(v, h0, h1, a8, l8);
+  const size_t plane = ((size_t)b * (COUT / 8) + cb * 2) * 2;  // (chunk 2cb, part 0)
+  out16[plane * plane_vox + vox] = h0;
+  out16[(plane + 1) * plane_vox + vox] = a8;
+  out16[(plane + 2) * plane_vox + vox] = h1;
+  out16[(plane + 3) * plane_vox + vox] = l8;
 }
 
 __device__ __forceinline__ void head_blend_16(const float (&v)[16], const FusedTail& t, const float* __restrict__ s_head,
@@ -293,6 +333,7 @@ struct UmmaConvParams {
   const float* bias;
   __half* out;
   int relu;
+  float acc_scale;  // f16f8 mode: 1 / (alpha * beta), the scale the operands carry (act_format.cuh); 1 otherwise
   int bstages;    // weight block stages in shared memory
   int bresident;  // 1: all 27*KG blocks stay resident (loaded once per CTA), 0: streamed through a ring
   int wide_map;   // 1: 5-D tensor map with the 16-byte record as inner dimension, 0: 4-D map over 8-byte elements
@@ -526,7 +567,7 @@ conv3_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             v[i] += __ldg(p.bias + cb * 16 + i);
-            if (p.relu) v[i] = fmaxf(v[i], 0.f);
+            if (p.relu) v[i] = relu_nan(v[i]);
           }
           if (valid) {
             if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, z, y0 + row, x0 + col);
@@ -787,7 +828,7 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               v[i] += __ldg(p.bias + cb * 16 + i);
-              if (p.relu) v[i] = fmaxf(v[i], 0.f);
+              if (p.relu) v[i] = relu_nan(v[i]);
             }
             if (valid) {
               if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, pz, y0 + row, x0 + col);
@@ -840,7 +881,7 @@ constexpr int kTsACol0 = 384;     // groups live at columns [384, 512)
 constexpr int kTsAccCols = 192;   // accumulator columns per buffer (2 buffers)
 constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsGroups) * 8 + 16 + 640;
 
-template <int CIN, int COUT, bool SPLIT, bool TAIL>
+template <int CIN, int COUT, bool SPLIT, bool TAIL, bool F8 = false>
 __global__ void __launch_bounds__(kThreadsTSTail, 1)
 conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const UmmaConvParams p) {
@@ -1023,8 +1064,14 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                       if (dx && !CFB_ABL(p, 8)) tc_shift_down(a_tm);
                       const uint32_t bt = bk + dx * (3 * Cfg::BSTAGE >> 4);
                       if (CFB_ABL(p, 16)) continue;
-                      tc_mma_f16_ta(d, a_tm, desc(b_lbo | bt), idesc, 1u);                                  // x w_hi
-                      if (SPLIT && part == 0) tc_mma_f16_ta(d, a_tm, desc(b_lbo | (bt + 3 * COUT)), idesc, 1u);  // a_hi x w_lo
+                      if constexpr (F8) {
+                        // f16f8: H x WH in fp16, then [A8 | L8] x [WL8 ; W8] (K = 32) in e4m3 -- two products per multiply
+                        if (part == 0) tc_mma_f16_ta(d, a_tm, desc(b_lbo | bt), idesc, 1u);
+                        else tc_mma_f8_ta(d, a_tm, desc(b_lbo | (bt + 3 * COUT)), idesc, 1u);
+                      } else {
+                        tc_mma_f16_ta(d, a_tm, desc(b_lbo | bt), idesc, 1u);                                  // x w_hi
+                        if (SPLIT && part == 0) tc_mma_f16_ta(d, a_tm, desc(b_lbo | (bt + 3 * COUT)), idesc, 1u);  // a_hi x w_lo
+                      }
                     }
                   }
                 }
@@ -1152,13 +1199,18 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            if constexpr (F8) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= p.acc_scale;
+            }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               v[i] += __ldg(p.bias + cb * 16 + i);
-              if (p.relu) v[i] = fmaxf(v[i], 0.f);
+              if (p.relu) v[i] = relu_nan(v[i]);
             }
             if (valid && !CFB_ABL(p, 1)) {
               if constexpr (TAIL) head_blend_16(v, p.tail, s_head, pp, pz, y0 + row, x0 + col);
+              else if constexpr (F8) store_cp8_16_f8<COUT>(v, cb, b, vox, plane_vox, out16);
               else store_cp8_16<COUT, SPLIT>(v, cb, b, vox, plane_vox, out16);
             }
           }
@@ -1206,9 +1258,10 @@ struct UmmaConvTParams {
   const __half* wpacked;
   const float* bias;
   __half* out;
+  float acc_scale;   // f16f8 mode: 1 / (alpha * beta)
 };
 
-template <int CIN, int COUT, bool SPLIT>
+template <int CIN, int COUT, bool SPLIT, bool F8 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParams p) {
   constexpr int P = SPLIT ? 2 : 1;
@@ -1292,8 +1345,14 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
           uint32_t a_lo = a0 + (uint32_t)ks * 2u * P * plane16;
           uint32_t d = tmem_base + buf * kBufCols;
           for (int g = 0; g < p.G; ++g, a_lo += 128, d += N1) {
-            tc_mma_f16(d, desc(a_lo), bdesc, IDESC1, ks == 0 ? 0u : 1u);
-            if (SPLIT) tc_mma_f16(d, desc(a_lo + plane16), bdesc, IDESC2, 1u);
+            if constexpr (F8) {
+              // H x WH (rows 0..N2) in fp16, [A8 | L8] x [WL8 ; W8] (rows N2..2 N2, K = 32) in e4m3, same accumulator columns
+              tc_mma_f16(d, desc(a_lo), bdesc, IDESC2, ks == 0 ? 0u : 1u);
+              tc_mma_f8(d, desc(a_lo + plane16), bdesc + (uint64_t)N2, IDESC2, 1u);
+            } else {
+              tc_mma_f16(d, desc(a_lo), bdesc, IDESC1, ks == 0 ? 0u : 1u);
+              if (SPLIT) tc_mma_f16(d, desc(a_lo + plane16), bdesc, IDESC2, 1u);
+            }
           }
         }
         tc_commit(BAR(3 + slot));
@@ -1326,7 +1385,7 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
             uint32_t r[16];
             tc_ld16(taddr + t * COUT + cb * 16, r);
             float v[16];
-            if (SPLIT) {
+            if (SPLIT && !F8) {
               uint32_t r2[16];
               tc_ld16(taddr + N2 + t * COUT + cb * 16, r2);
               tc_wait_ld();
@@ -1335,11 +1394,12 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
             } else {
               tc_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * (F8 ? p.acc_scale : 1.0f);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + cb * 16 + i);
-            if (valid) {
+            if (valid && F8) store_cp8_16_f8<COUT>(v, cb, b, ovox, oplane_vox, out16);
+            if (valid && !F8) {
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 float hi[8];
@@ -1590,7 +1650,7 @@ constexpr int kMaxSmem = 232448;  // 227 KB
 //   (halo amplification of the z-plane loads)/2 + (M-tile positions per useful output), scaled by
 //   the wave quantisation of the grid, + a penalty for shallow weight rings.
 template <int CIN, int COUT, bool SPLIT>
-std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
+std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count, bool ts_only = false) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
   std::vector<ConvTile> out;
   const int ty_cap = std::min(16, (sz.y + 1) & ~1);
@@ -1663,7 +1723,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
     }
   }
   // z-stacked + TMEM-shift variants: M tiles of 120 positions, accumulators G * T * NB <= 224 columns per buffer
-  if (!getenv("CFB_NO_TSHIFT") && !getenv("CFB_NO_ZSTACK")) {
+  if (ts_only || (!getenv("CFB_NO_TSHIFT") && !getenv("CFB_NO_ZSTACK"))) {
     for (auto& e : xts) {
       const int XT = e.first, pitch = XT + 2;
       for (int T : {2, 3, 4, 6, 8}) {
@@ -1700,9 +1760,14 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
       }
     }
   }
+  if (ts_only) {  // f16f8 mode: only the TMEM-shift kernel implements the mixed fp16 / e4m3 products
+    std::vector<ConvTile> only;
+    for (const ConvTile& t : out) if (t.shift) only.push_back(t);
+    out.swap(only);
+  }
   if (const char* force = getenv("CFB_FORCE_ZSTACK")) {  // tests: exercise one kernel variant only
     const int T = atoi(force);
-    const bool want_shift = getenv("CFB_FORCE_TSHIFT") != nullptr;
+    const bool want_shift = ts_only || getenv("CFB_FORCE_TSHIFT") != nullptr;
     std::vector<ConvTile> only;
     for (const ConvTile& t : out) if (t.T == T && t.shift == want_shift) only.push_back(t);
     if (!only.empty()) out.swap(only);
@@ -1713,7 +1778,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count) {
 
 int sm_count();
 
-template <int CIN, int COUT, bool SPLIT>
+template <int CIN, int COUT, bool SPLIT, bool F8 = false>
 void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w,
                  __half* out, int nb, Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail = nullptr) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
@@ -1734,6 +1799,8 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   p.slot_stride = (uint32_t)((Cfg::NPL * (size_t)p.plane_stride + 127) / 128 * 128);
   p.planes_a = ca / 8; p.planes_b = cb / 8;
   p.wpacked = w.w; p.wpacked_zs = w.w_zs; p.wpacked_ts = w.w_ts; p.bias = w.bias; p.out = out; p.relu = relu ? 1 : 0;
+  p.acc_scale = w.acc_scale;
+  if (F8 && !t.shift) throw std::runtime_error("the f16f8 mode runs on the TMEM-shift kernel only");
   p.T = t.T;
   {
     static const int max_iss = [] { const char* e = std::getenv("CFB_TS_NISS"); return e ? atoi(e) : kTsMaxIssuers; }();
@@ -1781,7 +1848,7 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   if (tail) {
     if constexpr (CIN == 16 && COUT == 16) {
       p.tail = *tail;
-      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, true>, kThreadsTSTail);
+      if (t.shift) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, true, F8>, kThreadsTSTail);
       else if (t.T) run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, true>);
       else run(conv3_umma_kernel<CIN, COUT, SPLIT, true>);
       return;
@@ -1790,7 +1857,7 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
     }
   }
   if (t.shift) {
-    run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false>, kThreadsTS);
+    run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false, F8>, kThreadsTS);
     return;
   }
   if (t.T) {
@@ -1816,13 +1883,13 @@ int sm_count() {
 
 // First launch of a (layer, size, batch): time the most promising tilings on the real buffers (every
 // tiling computes bit-identical results) and cache the winner in the layer's PackedConv.
-template <int CIN, int COUT, bool SPLIT>
+template <int CIN, int COUT, bool SPLIT, bool F8 = false>
 void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
                 Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail) {
   const uint64_t key = ((uint64_t)sz.z << 48) ^ ((uint64_t)sz.y << 32) ^ ((uint64_t)sz.x << 16) ^ (uint64_t)nb;
   auto it = w.tuned->find(key);
   if (it == w.tuned->end()) {
-    std::vector<ConvTile> cands = enumerate_tiles<CIN, COUT, SPLIT>(nb, sz, sm_count());
+    std::vector<ConvTile> cands = enumerate_tiles<CIN, COUT, SPLIT>(nb, sz, sm_count(), F8);
     if (cands.empty()) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
     ConvTile best = cands[0];
     const int64_t work = (int64_t)nb * vol(sz);
@@ -1847,9 +1914,9 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       cands.swap(pick);
       const size_t n = cands.size();
       for (size_t i = 0; i < n; ++i) {
-        launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
+        launch_tile<CIN, COUT, SPLIT, F8>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
         CFB_CUDA(cudaEventRecord(e0, s));
-        launch_tile<CIN, COUT, SPLIT>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+        launch_tile<CIN, COUT, SPLIT, F8>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
         CFB_CUDA(cudaEventRecord(e1, s));
         CFB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
@@ -1873,14 +1940,14 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
 #ifdef CFB_TS_TRACE
   g_trace_print = getenv("CFB_TS_TRACE_PRINT") != nullptr;
 #endif
-  launch_tile<CIN, COUT, SPLIT>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
+  launch_tile<CIN, COUT, SPLIT, F8>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
 #ifdef CFB_TS_TRACE
   g_trace_print = false;
 #endif
 }
 
 
-template <int CIN, int COUT, bool SPLIT>
+template <int CIN, int COUT, bool SPLIT, bool F8 = false>
 void launch_convT_cfg(const __half* in, const PackedConv& w, __half* out, int nb, Int3 sz, cudaStream_t s) {
   constexpr int P = SPLIT ? 2 : 1;
   constexpr int NPL = P * CIN / 8, N1 = 4 * P * COUT, WBYTES = N1 * CIN * 2;
@@ -1899,22 +1966,22 @@ void launch_convT_cfg(const __half* in, const PackedConv& w, __half* out, int nb
   p.planes = CIN / 8;
   p.plane_stride = (uint32_t)(p.TY * p.XT * 16);
   p.slot_stride = (uint32_t)((NPL * (size_t)p.plane_stride + 127) / 128 * 128);
-  p.wpacked = w.w; p.bias = w.bias; p.out = out;
+  p.wpacked = w.w; p.bias = w.bias; p.out = out; p.acc_scale = w.acc_scale;
   const size_t smem = (size_t)kRing * p.slot_stride + WBYTES + 128 + kTailPad + 128;
   if (smem > (size_t)kMaxSmem) throw std::runtime_error("convT_umma: shared memory exceeded");
   const CUtensorMap mapA = make_map(in, nb * p.planes * P, sz, p.XT, p.TY, p.planes * P, /*wide=*/false);
-  auto kern = convT_umma_kernel<CIN, COUT, SPLIT>;
+  auto kern = convT_umma_kernel<CIN, COUT, SPLIT, F8>;
   CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, p);
   CFB_LAUNCH_CHECK();
 }
 
-template <bool SPLIT>
+template <bool SPLIT, bool F8 = false>
 void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb, Int3 sz,
               bool relu, cudaStream_t s, const FusedTail* tail) {
   const int cin = ca + cb, cout = w.cout;
 #define CFB_CASE(CI, CO) \
-  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
+  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT, F8>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
   CFB_CASE(16, 16) CFB_CASE(16, 32) CFB_CASE(32, 32) CFB_CASE(32, 64) CFB_CASE(64, 64) CFB_CASE(64, 32) CFB_CASE(32, 16)
 #undef CFB_CASE
   throw std::runtime_error("conv3_umma: unsupported channel configuration " + std::to_string(cin) + "->" + std::to_string(cout));
@@ -1932,15 +1999,26 @@ void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, c
     ft.channels = tail->channels; ft.op = tail->out_patch; ft.crop = tail->crop; ft.os = tail->out_size;
     ft.scale = tail->scale;
   }
-  if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
+  if (w.fmt == kFmtF16F8) dispatch<true, true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
+  else if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
   else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
 // Weight packing (host)
 // ------------------------------------------------------------------------------------------
-void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out) {
+// power of two >= the largest |w| of a layer (f16f8 mode: beta = 2^14 / wmax', act_format.cuh)
+static float weight_beta(const float* w, size_t n) {
+  float wmax = 0.f;
+  for (size_t i = 0; i < n; ++i) wmax = std::max(wmax, std::fabs(w[i]));
+  if (!(wmax > 0.f) || !std::isfinite(wmax)) return 16384.0f;
+  return 16384.0f / std::exp2(std::ceil(std::log2(wmax)));
+}
+static uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+
+void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int fmt, PackedConv& out) {
   free_packed(out);
+  const int parts = fmt_planes(fmt);
   const int KB = cin >= 32 ? 32 : 16, KG = cin / KB, NB = parts * cout;
   const size_t block = (size_t)NB * KB;  // halves
   std::vector<__half> buf((size_t)27 * KG * block);
@@ -1956,7 +2034,7 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
             const __half val = n < cout ? hi : __float2half_rn(wv - __half2float(hi));
             buf[((size_t)t * KG + g) * block + ((size_t)kc * NB + n) * 8 + e] = val;
           }
-  out.cin = cin; out.cout = cout; out.parts = parts;
+  out.cin = cin; out.cout = cout; out.parts = parts; out.fmt = fmt;
   out.tuned = std::make_shared<std::map<uint64_t, ConvTile>>();
   out.bytes = buf.size() * sizeof(__half);
   CFB_CUDA(cudaMalloc(&out.w, out.bytes));
@@ -1999,6 +2077,34 @@ void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout
                   ts[(((size_t)dy * KG + g) * 3 + dx) * (3 * block) + ((size_t)kc * 3 * NB + row) * 8 + e] =
                       part == 0 ? hi : __float2half_rn(wv - __half2float(hi));
                 }
+  if (fmt == kFmtF16F8) {
+    // f16f8 (act_format.cuh): part-0 rows = WH = fp16(w beta); part-1 rows hold e4m3 bytes, K step ks = 16-byte chunks
+    // (2 ks) = WL8 = e4m3((w beta - WH) mu) and (2 ks + 1) = W8 = e4m3(w delta) of the SAME 16 channels
+    const float beta = weight_beta(h_w, (size_t)cout * cin * 27), delta = beta / kActLambda;
+    out.acc_scale = 1.0f / (kActAlpha * beta);
+    uint8_t* tb = reinterpret_cast<uint8_t*>(ts.data());
+    for (int dy = 0; dy < 3; ++dy)
+      for (int g = 0; g < KG; ++g)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int kc = 0; kc < KB / 8; ++kc)
+            for (int zi = 0; zi < 3; ++zi)
+              for (int co = 0; co < cout; ++co) {
+                const int t = (2 - zi) * 9 + dy * 3 + dx;
+                const size_t blk0 = (((size_t)dy * KG + g) * 3 + dx) * (3 * block);
+                const size_t row_hi = (size_t)zi * cout + co, row_p1 = (size_t)3 * cout + row_hi;
+                for (int e = 0; e < 8; ++e) {
+                  const int ci = g * KB + kc * 8 + e;
+                  ts[blk0 + ((size_t)kc * 3 * NB + row_hi) * 8 + e] = __float2half_rn(h_w[((size_t)co * cin + ci) * 27 + t] * beta);
+                }
+                uint8_t* dst = tb + 2 * (blk0 + ((size_t)kc * 3 * NB + row_p1) * 8);
+                for (int j = 0; j < 16; ++j) {
+                  const int ci = g * KB + (kc / 2) * 16 + j;
+                  const float wb = h_w[((size_t)co * cin + ci) * 27 + t] * beta;
+                  const float wl = wb - __half2float(__float2half_rn(wb));
+                  dst[j] = (kc & 1) ? to_e4m3(h_w[((size_t)co * cin + ci) * 27 + t] * delta) : to_e4m3(wl * kWgtMu);
+                }
+              }
+  }
   CFB_CUDA(cudaMalloc(&out.w_ts, ts.size() * sizeof(__half)));
   CFB_CUDA(cudaMemcpy(out.w_ts, ts.data(), ts.size() * sizeof(__half), cudaMemcpyHostToDevice));
 }
@@ -2007,6 +2113,7 @@ void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int n
   const bool split = w.parts == 2;
 #define CFB_CASE(CI, CO)                                                                     \
   if (w.cin == CI && w.cout == CO) {                                                         \
+    if (w.fmt == kFmtF16F8) return launch_convT_cfg<CI, CO, true, true>(in, w, out, nb, in_size, s); \
     if (split) return launch_convT_cfg<CI, CO, true>(in, w, out, nb, in_size, s);            \
     return launch_convT_cfg<CI, CO, false>(in, w, out, nb, in_size, s);                      \
   }
@@ -2015,8 +2122,9 @@ void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int n
   throw std::runtime_error("convT_umma: unsupported channel configuration");
 }
 
-void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out) {
+void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int fmt, PackedConv& out) {
   free_packed(out);
+  const int parts = fmt_planes(fmt);
   const int N1 = 4 * parts * cout, N2 = 4 * cout;
   std::vector<__half> buf((size_t)N1 * cin);
   for (int kc = 0; kc < cin / 8; ++kc)
@@ -2028,6 +2136,24 @@ void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout
         const __half hi = __float2half_rn(wv);
         buf[((size_t)kc * N1 + n) * 8 + e] = n < N2 ? hi : __float2half_rn(wv - __half2float(hi));
       }
+  out.fmt = fmt;
+  if (fmt == kFmtF16F8) {  // rows 0..N2: WH; rows N2..2 N2: e4m3 bytes, chunk 2 ks = WL8, chunk 2 ks + 1 = W8 (16 channels of K step ks)
+    const float beta = weight_beta(h_w, (size_t)cin * cout * 4), delta = beta / kActLambda;
+    out.acc_scale = 1.0f / (kActAlpha * beta);
+    uint8_t* bb = reinterpret_cast<uint8_t*>(buf.data());
+    for (int kc = 0; kc < cin / 8; ++kc)
+      for (int n = 0; n < N2; ++n) {
+        const int t = n / cout, co = n % cout;
+        for (int e = 0; e < 8; ++e)
+          buf[((size_t)kc * N1 + n) * 8 + e] = __float2half_rn(h_w[((size_t)(kc * 8 + e) * cout + co) * 4 + t] * beta);
+        uint8_t* dst = bb + 2 * (((size_t)kc * N1 + N2 + n) * 8);
+        for (int j = 0; j < 16; ++j) {
+          const int ci = (kc / 2) * 16 + j;
+          const float w0 = h_w[((size_t)ci * cout + co) * 4 + t], wb = w0 * beta;
+          dst[j] = (kc & 1) ? to_e4m3(w0 * delta) : to_e4m3((wb - __half2float(__float2half_rn(wb))) * kWgtMu);
+        }
+      }
+  }
   out.cin = cin; out.cout = cout; out.parts = parts;
   out.tuned = std::make_shared<std::map<uint64_t, ConvTile>>();
   out.bytes = buf.size() * sizeof(__half);
@@ -2037,8 +2163,9 @@ void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout
   CFB_CUDA(cudaMemcpy(out.bias, h_bias, cout * sizeof(float), cudaMemcpyHostToDevice));
 }
 
-void pack_first_conv_weights(const float* h_w, const float* h_bias, int parts, PackedConv& out) {
+void pack_first_conv_weights(const float* h_w, const float* h_bias, int fmt, PackedConv& out) {
   free_packed(out);
+  const int parts = fmt_planes(fmt);
   const int NBR = 16 * parts;
   std::vector<__half> buf((size_t)4 * NBR * 8, __float2half_rn(0.f));
   for (int c = 0; c < 4; ++c)

@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 
+#include "act_format.cuh"
 #include "common.cuh"
 
 namespace cfb {
@@ -39,11 +40,13 @@ struct PackedConv {
   __half* w_ts = nullptr;  // device, (dy, kg) triples of z-stacked blocks for the TMEM-shift kernel
   float* bias = nullptr;
   int cin = 0, cout = 0, parts = 1;
+  int fmt = 0;             // ActFmt of the activations this layer reads and writes (act_format.cuh)
+  float acc_scale = 1.0f;  // f16f8: 1 / (alpha * beta), applied to the accumulator by the epilogue
   size_t bytes = 0;
   std::shared_ptr<std::map<uint64_t, ConvTile>> tuned;  // autotuned tiling per (size, batch)
 };
 
-void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out);
+void pack_conv3_weights(const float* h_w, const float* h_bias, int cin, int cout, int fmt, PackedConv& out);  // fmt: ActFmt
 void free_packed(PackedConv& p);
 
 // One 3x3x3 convolution + bias + ReLU on tcgen05.  Input = channel concat of srcA (ca channels)
@@ -65,14 +68,14 @@ void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, c
 
 // ConvTranspose kernel = stride = (1,2,2) on tcgen05 (GEMM over input voxels + scatter epilogue).
 // h_w: (cin, cout, 1, 2, 2) fp32.  in: CP8 (nb, cin) of size in_size; out: CP8 (nb, cout) of (Z, 2Y, 2X).
-void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int parts, PackedConv& out);
+void pack_convT_weights(const float* h_w, const float* h_bias, int cin, int cout, int fmt, PackedConv& out);
 void launch_convT_umma(const __half* in, const PackedConv& w, __half* out, int nb, Int3 in_size, cudaStream_t s);
 
 // First layer (Cin = 1 -> 16) on tcgen05, fused with uint8 patch extraction (+ /255, bias, ReLU -> CP8).
 // EXPERIMENTAL (env CFB_UMMA_FIRST_CONV=1): correct, but the per-thread im2col gather is latency-bound
 // (27.7 ms vs 7.8 ms per 99 patches for the CUDA-core kernel), so the CUDA-core kernel stays the default.
 // h_w: (16, 1, 3, 3, 3) fp32.
-void pack_first_conv_weights(const float* h_w, const float* h_bias, int parts, PackedConv& out);
+void pack_first_conv_weights(const float* h_w, const float* h_bias, int fmt, PackedConv& out);
 void launch_first_conv_umma(const void* chunk_u8, Int3 chunk_size, const PatchPos* patches, int nb, Int3 patch,
                             const PackedConv& w, __half* out, cudaStream_t s);
 

@@ -24,7 +24,8 @@ const Spec kSpecs[] = {
 }  // namespace
 
 void Network::configure(int precision, Int3 patch, int batch) {
-  if (precision != CFB_PRECISION_F32_SIMT && precision != CFB_PRECISION_F16X3_UMMA && precision != CFB_PRECISION_F16_UMMA)
+  if (precision != CFB_PRECISION_F32_SIMT && precision != CFB_PRECISION_F16X3_UMMA && precision != CFB_PRECISION_F16_UMMA &&
+      precision != CFB_PRECISION_F16F8_UMMA)
     throw std::invalid_argument("unknown precision mode");
   precision_ = precision;
   patch_ = patch;
@@ -109,9 +110,9 @@ bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int 
     CFB_CUDA(cudaMemcpy(L.w, wi->second.data(), wi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
     CFB_CUDA(cudaMemcpy(L.bias, bi->second.data(), bi->second.size() * sizeof(float), cudaMemcpyHostToDevice));
     if (umma() && sp.taps == 27 && sp.cin >= 16)
-      pack_conv3_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
+      pack_conv3_weights(wi->second.data(), bi->second.data(), sp.cin, cout, fmt(), L.packed);
     if (umma() && sp.taps == 27 && sp.cin == 1) {
-      pack_first_conv_weights(wi->second.data(), bi->second.data(), parts(), L.packed);
+      pack_first_conv_weights(wi->second.data(), bi->second.data(), fmt(), L.packed);
       if (cout == 16) {
         for (int t = 0; t < 27; ++t)
           for (int c = 0; c < 16; ++c) first_w_.w[t][c] = wi->second[(size_t)c * 27 + t];
@@ -119,7 +120,7 @@ bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int 
       }
     }
     if (umma() && sp.taps == 4)
-      pack_convT_weights(wi->second.data(), bi->second.data(), sp.cin, cout, parts(), L.packed);
+      pack_convT_weights(wi->second.data(), bi->second.data(), sp.cin, cout, fmt(), L.packed);
     layers_[sp.name] = L;
   }
   if (num_output_channels > cnet_) { err = "the network produces fewer channels than num_output_channels"; return false; }
@@ -201,11 +202,11 @@ int Network::forward(int nb, cudaStream_t s) {
 int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s,
                          bool with_head, const ConvTail* tail) {
   const Int3 s0 = patch_, s1{patch_.z, patch_.y / 2, patch_.x / 2}, s2{patch_.z, patch_.y / 4, patch_.x / 4};
-  const int P = parts();
+  const int P = fmt();  // the CUDA-core CP8 kernels take the number format
   {
     const ConvLayer& L = layers_.at("enc0.0");
     prof_begin("enc0.0", s);
-    if (chunk && in_dtype == CFB_DTYPE_U8 && getenv("CFB_UMMA_FIRST_CONV")) launch_first_conv_umma(chunk, cs, patches, nb, s0, L.packed, h_e0a_, s);
+    if (chunk && in_dtype == CFB_DTYPE_U8 && getenv("CFB_UMMA_FIRST_CONV") && P != kFmtF16F8) launch_first_conv_umma(chunk, cs, patches, nb, s0, L.packed, h_e0a_, s);
     else if (chunk) launch_first_conv_cp8(chunk, in_dtype, cs, patches, nb, s0, L.w, L.bias, h_e0a_, P, s,
                                           getenv("CFB_FIRST_CONV_SMEM_W") ? nullptr : &first_w_);
     else launch_first_conv_cp8_from_patches(buf_in_, nb, s0, L.w, L.bias, h_e0a_, P, s);
@@ -280,7 +281,7 @@ int Network::blend(Int3 op, Int3 crop, const float* mask, const PatchPos* patche
   if (umma()) {
     const ConvLayer& L = layers_.at("head");
     prof_begin("head+blend", s);
-    launch_head_blend_cp8(h_d0_, L.w, L.bias, 16, cnet_, parts(), patch_, op, crop, mask, patches, nb, out, channels, out_size, scale, s);
+    launch_head_blend_cp8(h_d0_, L.w, L.bias, 16, cnet_, fmt(), patch_, op, crop, mask, patches, nb, out, channels, out_size, scale, s);
     prof_end(s);
     return 1;
   }
@@ -316,12 +317,12 @@ int Network::debug_conv3(const float* h_in, int cin, Int3 size, const float* h_w
     CFB_CUDA(cudaMalloc(&c_in, (size_t)cin * P * v * 2));
     CFB_CUDA(cudaMalloc(&c_out, (size_t)cout * P * v * 2));
     PackedConv pk;
-    pack_conv3_weights(h_w, h_b, cin, cout, P, pk);
-    launch_planar_to_cp8(d_in, c_in, cin, P, 1, size, s);
+    pack_conv3_weights(h_w, h_b, cin, cout, fmt(), pk);
+    launch_planar_to_cp8(d_in, c_in, cin, fmt(), 1, size, s);
     // exercise the two-source (concat) path whenever the channel count allows it
     const int ca = cin >= 32 ? cin / 2 : cin, cb = cin - ca;
     launch_conv3_umma(c_in, ca, cb ? c_in + (size_t)ca * P * v : nullptr, cb, pk, c_out, 1, size, relu, s);
-    launch_cp8_to_planar(c_out, d_out, cout, P, 1, size, s);
+    launch_cp8_to_planar(c_out, d_out, cout, fmt(), 1, size, s);
     CFB_CUDA(cudaMemcpyAsync(h_out, d_out, (size_t)cout * v * 4, cudaMemcpyDeviceToHost, s));
     cudaError_t err = cudaStreamSynchronize(s);
     cudaFree(c_in); cudaFree(c_out); free_packed(pk);

@@ -55,7 +55,9 @@ class Network {
   int forward_cp8(const void* chunk, int in_dtype, Int3 chunk_size, const PatchPos* patches, int nb, cudaStream_t s,
                   bool with_head, const ConvTail* tail = nullptr);
   bool umma() const { return precision_ != 0; }
-  int parts() const { return precision_ == 1 ? 2 : 1; }
+  // activation number format of the tcgen05 path (act_format.cuh) and its planes per 8-channel chunk
+  int fmt() const { return precision_ == 1 ? kFmtF16x2 : (precision_ == 3 ? kFmtF16F8 : kFmtF16); }
+  int parts() const { return fmt_planes(fmt()); }
 
   struct Span { int id; cudaEvent_t a, b; };
   void prof_begin(const char* name, cudaStream_t s);

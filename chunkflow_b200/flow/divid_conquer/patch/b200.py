@@ -62,7 +62,8 @@ def precision_code(dtype: str = "float32", precision=None) -> int:
     float16 as a lower-precision option, flow.py:1871-1874).  ``precision`` (or env
     CHUNKFLOW_B200_PRECISION) forces one of 'simt' (fp32 FFMA on CUDA cores), 'f16x3', 'f16'.
     """
-    names = {"simt": _native.PRECISION_F32_SIMT, "f16x3": _native.PRECISION_F16X3_UMMA, "f16": _native.PRECISION_F16_UMMA}
+    names = {"simt": _native.PRECISION_F32_SIMT, "f16x3": _native.PRECISION_F16X3_UMMA, "f16": _native.PRECISION_F16_UMMA,
+             "f16f8": _native.PRECISION_F16F8_UMMA}
     precision = precision or os.environ.get("CHUNKFLOW_B200_PRECISION")
     if precision is not None:
         if isinstance(precision, int):

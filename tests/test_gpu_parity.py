@@ -97,7 +97,8 @@ def test_reference_test_time_augmentation_identity():
 
 
 @pytest.mark.parametrize("precision,dtype,atol", [(None, "float32", NET_ATOL_F32), ("simt", "float32", NET_ATOL_SIMT),
-                                                  ("f16x3", "float32", NET_ATOL_F32), (None, "float16", NET_ATOL_F16)])
+                                                  ("f16x3", "float32", NET_ATOL_F32), ("f16f8", "float32", NET_ATOL_F32),
+                                                  (None, "float16", NET_ATOL_F16)])
 def test_unet3l_golden(golden, precision, dtype, atol):
     """The reference's own `-f pytorch` CPU output (golden) against every precision mode."""
     g = golden("unet3l_small.npz")
@@ -178,6 +179,20 @@ def test_conv3_layer_tcgen05_tmem_shift_kernel(monkeypatch, zstack, cin, cout, s
     _conv3_case(_native.PRECISION_F16X3_UMMA, cin, cout, size, 5e-5)
     if cin == 16:
         _conv3_case(_native.PRECISION_F16_UMMA, cin, cout, size, 1e-2)
+
+
+@pytest.mark.parametrize("cin,cout,size", UMMA_CASES)
+def test_conv3_layer_tcgen05_f16f8_against_torch(cin, cout, size):
+    # fp16 main product + one e4m3 (K = 32) product for both correction terms: ~2^-16 relative per product
+    # (inputs ~N(0,1), outputs of magnitude ~5: fp16 alone is asserted at 1e-2 below, the hi/lo split at 5e-5)
+    _conv3_case(_native.PRECISION_F16F8_UMMA, cin, cout, size, 4e-4)
+
+
+@pytest.mark.parametrize("zstack", ["2", "3", "4"])
+@pytest.mark.parametrize("cin,cout,size", [(16, 16, (9, 16, 70)), (32, 32, (5, 12, 20)), (64, 32, (4, 16, 16)), (16, 16, (1, 7, 9))])
+def test_conv3_layer_f16f8_forced_zstack(monkeypatch, zstack, cin, cout, size):
+    monkeypatch.setenv("CFB_FORCE_ZSTACK", zstack)
+    _conv3_case(_native.PRECISION_F16F8_UMMA, cin, cout, size, 4e-4)
 
 
 @pytest.mark.parametrize("cin,cout,size", UMMA_CASES[:4])

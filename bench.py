@@ -272,6 +272,7 @@ def main():
                     "reference arm spreads >= 26 patches over its timed steps)")
     ap.add_argument("--no-split-chunk", action="store_true", help="N > 1: skip the config-#5 block (one chunk split over the ranks)")
     ap.add_argument("--no-pageable", action="store_true")
+    ap.add_argument("--no-alt-precision", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -411,7 +412,8 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md)",
                 "traffic": traffic, "launches": dom_launches, "ms_per_launch": dom_ms / max(dom_launches, 1),
                 "algorithmic_flop_per_launch": dom_flop_per_launch,
-                "note": "the fp16 hi/lo split (f16x3) executes 3x these algorithmic FLOPs on the tensor pipe" + pipe_note +
+                "note": ("the f16f8 mode executes 2x these algorithmic FLOPs on the tensor pipe (one fp16 + one e4m3 K=32 product per multiply)"
+                         if eng.params.precision == 3 else "the fp16 hi/lo split (f16x3) executes 3x these algorithmic FLOPs on the tensor pipe") + pipe_note +
                         " (profiles/r01_ncu_full_summary.md)",
                 "conv_stack": {"achieved": conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0, "unit": "TFLOP/s",
                                "ms_per_chunk": conv_ms, "launches": conv_launches, "algorithmic_flop_per_chunk": conv_flop}}
@@ -480,7 +482,7 @@ def main():
         del plain, chunk
 
     # ---- CPU baseline (rank 0, N = 1) and parity of the GPU path on the SAME sub-chunk at the benchmarked geometry
-    cpu, parity = None, None
+    cpu, parity, cpu_sample = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ref = CpuReference(patch, overlap, threads)
         r = ref.run(chunk_shape, args.cpu_sample_patches or 12, 20260922)
@@ -495,7 +497,31 @@ def main():
         parity = {"max_abs": float(np.abs(got - r["output"]).max()), "tolerance": 1e-3,
                   "config": f"sub-chunk {'x'.join(map(str, r['sub']))} = {r['patches']} patches of the benchmarked geometry, batch "
                             f"{args.batch_size}, GPU result vs the CPU reference port (bit-identical to the reference's -f pytorch path)"}
-        del got, r
+        del got
+        cpu_sample = r
+
+    # ---- the other fp32-parity mode of the convolution stack, device-resident, for the record (rank 0, N = 1)
+    alt = None
+    if rank == 0 and world == 1 and not args.no_alt_precision and eng.params.precision in (1, 3):
+        other = "f16x3" if eng.params.precision == 3 else "f16f8"
+        inf2 = Inferencer(MODEL_FILE, None, patch, output_patch_overlap=overlap, num_output_channels=3, framework="b200",
+                          batch_size=args.batch_size, mask_output_chunk=True, device=local_rank, precision=other)
+        for _ in range(2):
+            inf2.engine.infer_chunk_device(d_in.data_ptr(), np.uint8, chunk_shape, d_out.data_ptr(), stream)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(min(args.steps, 3)):
+            inf2.engine.infer_chunk_device(d_in.data_ptr(), np.uint8, chunk_shape, d_out.data_ptr(), stream)
+        a1.record()
+        torch.cuda.synchronize()
+        alt_ms = a0.elapsed_time(a1) / min(args.steps, 3)
+        alt = {"precision": other, "ms_per_step": alt_ms, "value": nvox / (alt_ms / 1e3) / 1e6, "unit": "Mvoxels/s"}
+        if cpu_sample is not None:   # parity of this mode on the same sub-chunk as the main parity block
+            got2 = inf2(Chunk(cpu_sample["image"])).array
+            alt["parity_max_abs"] = float(np.abs(got2 - cpu_sample["output"]).max())
+            del got2
+        del inf2
+    cpu_sample = None
 
     # ---- BASELINE config #5: ONE 512x2048x2048 chunk split over the N ranks, halo planes exchanged over NCCL
     split = None
@@ -513,7 +539,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {0: "f32", 1: "f16x3", 2: "f16", 3: "f16f8"}[eng.params.precision], "precision_mode": precision,
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches) * args.steps,
-            "e2e_pageable": e2e_pageable, "parity": parity, "split_chunk": split,
+            "e2e_pageable": e2e_pageable, "parity": parity, "split_chunk": split, "alt_precision": alt,
             "roofline": roofline, "memory_kernels": mem, "kernel_ms_per_chunk": step_ms, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()

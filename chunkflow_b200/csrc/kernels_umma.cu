@@ -872,8 +872,12 @@ conv3_zs_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 // lane (k, i) <-> position 120 g + 30 k + i, i < 30 valid.
 // Weight blocks: (dy, kg) triples of the z-stacked blocks of dx = 0, 1, 2.
 // ------------------------------------------------------------------------------------------
-constexpr int kThreadsTS = 384;   // 12 warps: A producer, B producer, MMA issuer 0, 4 epilogue, 4 TMEM loaders, MMA issuer 1
-constexpr int kThreadsTSTail = 512;  // fused tail: 4 more epilogue warps
+#ifndef CFB_TS_LOADER_SETS
+#define CFB_TS_LOADER_SETS 1
+#endif
+constexpr int kTsLoaderSets = CFB_TS_LOADER_SETS;  // sets of 4 TMEM-loader warps; set s fills the A-tile groups n with n % sets == s
+constexpr int kThreadsTS = 384 + 128 * (kTsLoaderSets - 1);   // warps: A producer, B producer, MMA issuer 0, 4 epilogue, 4 TMEM loaders, MMA issuer 1 (, 4 more loaders)
+constexpr int kThreadsTSTail = 512;  // fused tail: 4 more epilogue warps (12..15) and ONE loader set (a 640-thread CTA would cap at 96 registers and spill)
 constexpr int kTsGroups = 4;      // at most: ring of A-tile GROUPS in TMEM (16 tiles / (P * G) of them); a group = all (part, tile) A tiles of one (plane, dy, K step)
 constexpr int kTsMaxIssuers = 2;   // measured: 3 or 4 issuers are no faster than 2 (the kernel is no longer issue bound)
 constexpr int kTsMaxTiles = 8;    // P * G <= 8 tiles of 8 columns per group
@@ -882,7 +886,7 @@ constexpr int kTsAccCols = 192;   // accumulator columns per buffer (2 buffers)
 constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsGroups) * 8 + 16 + 640;
 
 template <int CIN, int COUT, bool SPLIT, bool TAIL, bool F8 = false>
-__global__ void __launch_bounds__(kThreadsTSTail, 1)
+__global__ void __launch_bounds__(TAIL ? kThreadsTSTail : kThreadsTS, 1)
 conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const UmmaConvParams p) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
@@ -893,7 +897,8 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // along N here: a_hi x w_hi, a_hi x w_lo and a_lo x w_hi all accumulate into the same COUT columns of a plane
   // (half the TMEM per plane -> twice the z-stacking depth T, fewer tensor cycles and fewer weight bytes per tap).
   constexpr int KSTEPS = CIN / 16;
-  constexpr int kEpiSets = TAIL ? 2 : 1;  // the fused tail is epilogue bound: 8 epilogue warps (launched with 512 threads), else 4 (384)
+  constexpr int kEpiSets = TAIL ? 2 : 1;  // the fused tail is epilogue bound: 8 epilogue warps (launched with 512 threads), else 4
+  constexpr int LS = TAIL ? 1 : kTsLoaderSets;  // sets of four TMEM-loader warps
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
 
@@ -923,7 +928,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4); }  // plane slots are released by the 4 loader warps
+    for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 4 * LS); }  // plane slots are released by the loader warps
     for (int i = 0; i < p.bstages; ++i) { mbar_init(BAR(kBF + i), 1); mbar_init(BAR(kBE + i), p.niss); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(kAccF + i), p.niss); mbar_init(BAR(kAccE + i), 128 * kEpiSets); }
     for (int i = 0; i < kTsGroups; ++i) { mbar_init(BAR(kTF + i), 128); mbar_init(BAR(kTE + i), p.niss); }
@@ -1055,6 +1060,8 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #ifdef CFB_TS_TRACE
                 const long long tr_i0 = clock64();
 #endif
+                // (issuing the shifts and the MMAs of all tiles of a group interleaved -- all shifts of a dx step, then all its MMAs --
+                //  to space dependent instructions apart measured 15 % SLOWER on every layer: profiles/r02_ab_issue_order.txt)
                 for (int part = 0; part < P; ++part) {  // A tile part: 0 = hi, 1 = lo
                   uint32_t d = dcol0 + iss * dstep1;
                   uint32_t a_tm = a_grp + (uint32_t)part * G * 8;
@@ -1065,7 +1072,6 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                       const uint32_t bt = bk + dx * (3 * Cfg::BSTAGE >> 4);
                       if (CFB_ABL(p, 16)) continue;
                       if constexpr (F8) {
-                        // f16f8: H x WH in fp16, then [A8 | L8] x [WL8 ; W8] (K = 32) in e4m3 -- two products per multiply
                         if (part == 0) tc_mma_f16_ta(d, a_tm, desc(b_lbo | bt), idesc, 1u);
                         else tc_mma_f8_ta(d, a_tm, desc(b_lbo | (bt + 3 * COUT)), idesc, 1u);
                       } else {
@@ -1100,8 +1106,11 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
 #endif
     }
-  } else if (warp >= 7 && warp <= 10) {
+  } else if ((warp >= 7 && warp <= 10) || (LS == 2 && warp >= 12)) {
     // ---------------- TMEM loaders: shared-memory plane -> A tiles in tensor memory ----------------
+    // (the copy of a group is a latency chain -- ld.shared, tcgen05.st, wait::st, arrive --, so two sets of four
+    //  warps take alternate groups)
+    const uint32_t lset = warp >= 11 ? 1u : 0u;
     const int wq = warp & 3;                    // lane quarter this warp may access
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     const uint32_t pos_in_tile = (uint32_t)(30 * wq + lane);  // lane (k, i) <-> position 30 k + i
@@ -1111,6 +1120,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     uint32_t tgrp = 0, tparity = 1;  // parity of the previous release (none during the first round)
     uint32_t gcount = 0;
     const uint32_t ngroups = (uint32_t)p.ngroups, gstride = (uint32_t)(P * p.G * 8);
+    auto next_group = [&]() { ++gcount; if (++tgrp == ngroups) { tgrp = 0; tparity ^= 1; } };
     [[maybe_unused]] long long tr_slot = 0, tr_te = 0, tr_t0 = clock64();
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int z0 = item_of(item).z0, qlo = max(z0 - 1, 0), qhi = min(z0 + T, Z - 1);
@@ -1118,7 +1128,8 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         CFB_TRACE_WAIT(tr_slot, mbar_wait(BAR(slot), sparity));  // TMA has landed this z-plane
         const uint4* plane = sA16 + (size_t)slot * (p.slot_stride >> 4);
         for (int dy = 0; dy < 3; ++dy) {
-          for (int kstep = 0; kstep < KSTEPS; ++kstep, ++gcount) {
+          for (int kstep = 0; kstep < KSTEPS; ++kstep) {
+            if (LS == 2 && (gcount & 1u) != lset) { next_group(); continue; }  // the other set's group
             // one group = the P * G A tiles of this (plane, dy, K step): loads first, then the TMEM stores, one hand-off
             uint4 c0[kTsMaxTiles], c1[kTsMaxTiles];
             const uint4* src = plane + (size_t)(kstep * 2) * P * plane16 + dy * p.pitch + pos_in_tile;
@@ -1140,7 +1151,7 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(BAR(kTF + tgrp));
-            if (++tgrp == ngroups) { tgrp = 0; tparity ^= 1; }
+            next_group();
           }
         }
         // the tensor core never reads A from shared memory in this kernel: once this warp's copies of the plane are

@@ -18,6 +18,7 @@ Frameworks:
 from __future__ import annotations
 
 import os
+import sys
 from typing import Union
 from warnings import warn
 
@@ -30,28 +31,6 @@ from chunkflow_b200.lib.cartesian_coordinate import Cartesian, to_cartesian
 from .patch.base import PatchInferencerBase
 from .patch import b200 as b200_patch
 from .transform import TransformSequences
-
-
-def _empty_result(shape) -> np.ndarray:
-    """``np.empty(shape, float32)`` for the result chunk (the reference allocates ``np.zeros`` per call,
-    inferencer.py:190-198).  A 1024^3 result is 12.9 GB = 3.1 million 4 KB pages: first touch and, above all, the
-    later free of that many pages cost seconds inside a VM (measured 1.6 s for the munmap alone).  Large results are
-    therefore backed by an anonymous mapping advised to use transparent huge pages (2 MB); the array owns the
-    mapping and frees it when it is garbage collected, like any numpy array."""
-    nbytes = int(np.prod(shape)) * 4
-    if nbytes < (64 << 20):
-        return np.empty(shape, dtype=np.float32)
-    try:
-        import mmap
-        huge = 2 << 20
-        mm = mmap.mmap(-1, nbytes + huge)     # room to start on a 2 MB boundary
-        if hasattr(mm, 'madvise') and hasattr(mmap, 'MADV_HUGEPAGE'):
-            mm.madvise(mmap.MADV_HUGEPAGE)
-        base = np.frombuffer(mm, dtype=np.uint8)
-        skip = (-base.ctypes.data) % huge
-        return base[skip:skip + nbytes].view(np.float32).reshape(shape)
-    except (OSError, ValueError, ImportError):
-        return np.empty(shape, dtype=np.float32)
 
 
 class Inferencer(object):
@@ -310,7 +289,7 @@ class Inferencer(object):
             assert output_buffer.shape == tuple(self.output_size) and output_buffer.dtype == np.float32
             out = output_buffer
         else:
-            out = _empty_result(self.output_size)
+            out = self._result_array(self.output_size)
         try:
             if self.patch_inferencer is None:
                 self.engine.infer_chunk_host(arr, out)
@@ -327,6 +306,23 @@ class Inferencer(object):
             assert out.shape[0] == 4
             out = out[:-1]
         return Chunk(out, voxel_offset=output_voxel_offset, voxel_size=input_chunk.voxel_size)
+
+    def _result_array(self, shape) -> np.ndarray:
+        """A float32 array for the result chunk (the reference allocates one per call, inferencer.py:190-198).  A 1024^3
+        result is 12.9 GB = 3.1 million pages: inside a VM the first touch and above all the later ``munmap`` of that many
+        pages cost seconds (measured 1.6 s for the free alone, more with huge pages).  The last result array is therefore
+        kept and handed out AGAIN once the caller has dropped every reference to it (views and buffer exports hold
+        references, so a result that is still in use is never recycled); otherwise a new array is allocated."""
+        shape = tuple(int(v) for v in shape)
+        buf = getattr(self, '_last_result', None)
+        if buf is not None and buf.shape == shape and sys.getrefcount(buf) <= 3:  # self._last_result, buf, getrefcount's argument
+            return buf
+        buf = None
+        self._last_result = None           # release the old one before allocating (peak memory)
+        out = np.empty(shape, dtype=np.float32)
+        if out.nbytes >= (64 << 20):
+            self._last_result = out
+        return out
 
     def infer_device(self, input_chunk):
         """Extension: the same operator on a :class:`chunkflow_b200.chunk.device.DeviceChunk` --

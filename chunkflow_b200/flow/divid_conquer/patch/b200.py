@@ -56,11 +56,13 @@ def load_state_dict(convnet_model=None, convnet_weight_path=None) -> dict:
 def precision_code(dtype: str = "float32", precision=None) -> int:
     """``--dtype`` -> precision mode of the convolution stack.
 
-    float32 -> 'f16x3': tcgen05 tensor cores on fp16 hi/lo split operands with fp32 accumulation
-    (measured 3e-5 max-abs against the fp32 CPU reference -- the 1e-3 parity mode);
-    float16 -> 'f16': single-pass fp16 tensor cores, ~3e-3 max-abs (the reference documents
-    float16 as a lower-precision option, flow.py:1871-1874).  ``precision`` (or env
-    CHUNKFLOW_B200_PRECISION) forces one of 'simt' (fp32 FFMA on CUDA cores), 'f16x3', 'f16'.
+    float32 -> 'f16f8' (default): tcgen05 tensor cores, fp16 main product plus ONE e4m3 product of twice the K depth that
+    carries both hi/lo correction terms, fp32 accumulation -- two tensor-core products per multiply (csrc/act_format.cuh);
+    measured 1.7e-4 .. 2.1e-4 max-abs against the fp32 CPU reference (the bar is 1e-3).
+    'f16x3': fp16 hi/lo split operands, three products per multiply, 3e-5 .. 5e-5 max-abs, ~9 % slower.
+    float16 -> 'f16': single-pass fp16 tensor cores, ~3e-3 max-abs (the reference documents float16 as a lower-precision
+    option, flow.py:1871-1874).  ``precision`` (or env CHUNKFLOW_B200_PRECISION) forces one of 'simt' (fp32 FFMA on CUDA
+    cores), 'f16x3', 'f16f8', 'f16'.
     """
     names = {"simt": _native.PRECISION_F32_SIMT, "f16x3": _native.PRECISION_F16X3_UMMA, "f16": _native.PRECISION_F16_UMMA,
              "f16f8": _native.PRECISION_F16F8_UMMA}
@@ -72,7 +74,7 @@ def precision_code(dtype: str = "float32", precision=None) -> int:
     return DEFAULT_PRECISION[str(np.dtype(dtype))]
 
 
-DEFAULT_PRECISION = {"float32": _native.PRECISION_F16X3_UMMA, "float16": _native.PRECISION_F16_UMMA}
+DEFAULT_PRECISION = {"float32": _native.PRECISION_F16F8_UMMA, "float16": _native.PRECISION_F16_UMMA}
 
 
 class _DeviceBackend(PatchInferencerBase):

@@ -15,9 +15,11 @@ pytestmark = pytest.mark.gpu
 BLEND_ATOL = 2e-6
 # fp32 SIMT convolutions vs torch-CPU: different summation order only
 NET_ATOL_SIMT = 2e-5
-# default mode (tcgen05, fp16 hi/lo split, fp32 accumulate): measured 2e-5 .. 4e-5; the bar in
-# BASELINE.json's north_star is 1e-3 max-abs -- assert 5x tighter than that
-NET_ATOL_F32 = 2e-4
+# default mode 'f16f8' (tcgen05: fp16 main product + one e4m3 K=32 product carrying both hi/lo correction terms, fp32
+# accumulate): measured 0.9e-4 .. 2.1e-4; the bar in BASELINE.json's north_star is 1e-3 max-abs -- assert 2x tighter
+NET_ATOL_F32 = 5e-4
+# 'f16x3' (fp16 hi/lo split, three products per multiply): measured 2e-5 .. 5e-5 -- assert 5x tighter than the bar
+NET_ATOL_X3 = 2e-4
 NET_ATOL = 1e-3
 # single-pass fp16 (reference --dtype float16): operands and stored activations carry 11 bits
 NET_ATOL_F16 = 2e-2
@@ -97,7 +99,7 @@ def test_reference_test_time_augmentation_identity():
 
 
 @pytest.mark.parametrize("precision,dtype,atol", [(None, "float32", NET_ATOL_F32), ("simt", "float32", NET_ATOL_SIMT),
-                                                  ("f16x3", "float32", NET_ATOL_F32), ("f16f8", "float32", NET_ATOL_F32),
+                                                  ("f16x3", "float32", NET_ATOL_X3), ("f16f8", "float32", NET_ATOL_F32),
                                                   (None, "float16", NET_ATOL_F16)])
 def test_unet3l_golden(golden, precision, dtype, atol):
     """The reference's own `-f pytorch` CPU output (golden) against every precision mode."""
@@ -407,16 +409,17 @@ def _bench_geometry_case(unet_model, chunk_shape, patch, overlap, batch, seed):
     _oracle_threads()
     rng = np.random.default_rng(seed)
     img = rng.integers(0, 256, size=chunk_shape, dtype=np.uint8)
-    inf = _inferencer(model=MODEL_FILE, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
-                      batch_size=batch, framework="b200", mask_output_chunk=True)
-    out = inf(Chunk(img)).array
     o, _ = O.infer_chunk(img, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
                          framework="pytorch", model=unet_model)
-    err = float(np.abs(out - o).max())
-    print("bench-geometry parity", chunk_shape, patch, "patches", len(inf.patch_slices_list), "batch", batch, "max-abs", err)
-    assert out.shape == o.shape and err <= NET_ATOL_F32
-    again = inf(Chunk(img)).array    # cached tables, autotuned tilings: same result up to the order of the fp32 reductions
-    assert np.abs(again - out).max() <= 1e-5
+    for precision, atol in ((None, NET_ATOL_F32), ("f16x3", NET_ATOL_X3)):   # the default (benchmarked) mode and the hi/lo split
+        inf = _inferencer(model=MODEL_FILE, input_patch_size=patch, output_patch_overlap=overlap, num_output_channels=3,
+                          batch_size=batch, framework="b200", mask_output_chunk=True, precision=precision)
+        out = np.array(inf(Chunk(img)).array)
+        err = float(np.abs(out - o).max())
+        print("bench-geometry parity", chunk_shape, patch, "patches", len(inf.patch_slices_list), "batch", batch, precision, "max-abs", err)
+        assert out.shape == o.shape and err <= atol
+        again = inf(Chunk(img)).array    # cached tables, autotuned tilings: same result up to the order of the fp32 reductions
+        assert np.abs(again - out).max() <= 1e-5
 
 
 def test_bench_geometry_config3_batch12(unet_model):
@@ -499,7 +502,7 @@ def test_kernel_variants_agree(monkeypatch, unet_model):
     rng = np.random.default_rng(31)
     img = rng.integers(0, 256, size=(20, 96, 104), dtype=np.uint8)
     kw = dict(input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3, framework="b200",
-              batch_size=5)
+              batch_size=5, precision="f16x3")   # (the f16f8 mode exists on the TMEM-shift kernel only)
     ref, _ = O.infer_chunk(img, input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3,
                            framework="pytorch", model=unet_model)
     results = {}
@@ -514,6 +517,25 @@ def test_kernel_variants_agree(monkeypatch, unet_model):
         results[name] = _inferencer(model=MODEL_FILE, **kw)(Chunk(img)).array
         err = np.abs(results[name] - ref).max()
         print(name, "max-abs vs oracle", err)
-        assert err <= NET_ATOL_F32, name
+        assert err <= NET_ATOL_X3, name
     for name, arr in results.items():
         assert np.abs(arr - results["default"]).max() <= 5e-5, name
+
+
+def test_f16f8_unfused_and_cuda_core_paths(monkeypatch, unet_model):
+    """The default f16f8 number format through the kernels that are not on the default route: the unfused head+blend tail and the
+    CUDA-core transposed convolution (they decode / encode the H + A8 + L8 records through load8 / store8, kernels_cp8.cu)."""
+    rng = np.random.default_rng(41)
+    img = rng.integers(0, 256, size=(20, 96, 104), dtype=np.uint8)
+    kw = dict(input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3, framework="b200", batch_size=5)
+    ref, _ = O.infer_chunk(img, input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3,
+                           framework="pytorch", model=unet_model)
+    for env in ({}, {"CFB_NO_FUSED_TAIL": "1"}, {"CFB_SIMT_CONVT": "1"}, {"CFB_FORCE_ZSTACK": "2"}):
+        for k in ("CFB_NO_FUSED_TAIL", "CFB_SIMT_CONVT", "CFB_FORCE_ZSTACK"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = _inferencer(model=MODEL_FILE, **kw)(Chunk(img)).array
+        err = np.abs(out - ref).max()
+        print("f16f8", env, "max-abs vs oracle", err)
+        assert err <= NET_ATOL_F32, env

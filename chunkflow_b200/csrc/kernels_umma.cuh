@@ -79,6 +79,13 @@ void pack_first_conv_weights(const float* h_w, const float* h_bias, int fmt, Pac
 void launch_first_conv_umma(const void* chunk_u8, Int3 chunk_size, const PatchPos* patches, int nb, Int3 patch,
                             const PackedConv& w, __half* out, cudaStream_t s);
 
+// First layer on tcgen05 with the A operand in tensor memory (kernels_first.cu): uint8 chunk -> 16 channels in the activation
+// format `fmt` (ActFmt), fused with patch extraction, /255, bias and ReLU.  The default for uint8 chunks; env
+// CFB_SIMT_FIRST_CONV=1 selects the CUDA-core kernel below (also used for float32 chunks and pre-extracted patches).
+void pack_first_conv_ts_weights(const float* h_w, PackedConv& out);  // fills out.w_ts (call after pack_first_conv_weights)
+void launch_first_conv_ts(const void* chunk_u8, Int3 chunk_size, const PatchPos* patches, int nb, Int3 patch, const PackedConv& w,
+                          __half* out, int fmt, cudaStream_t s);
+
 // Layout conversion (tests / debug): planar fp32 (nb, C, Z,Y,X) <-> CP8.
 void launch_planar_to_cp8(const float* in, __half* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);
 void launch_cp8_to_planar(const __half* in, float* out, int channels, int parts, int nb, Int3 size, cudaStream_t s);

@@ -113,6 +113,7 @@ bool Network::load(const std::map<std::string, std::vector<float>>& host_w, int 
       pack_conv3_weights(wi->second.data(), bi->second.data(), sp.cin, cout, fmt(), L.packed);
     if (umma() && sp.taps == 27 && sp.cin == 1) {
       pack_first_conv_weights(wi->second.data(), bi->second.data(), fmt(), L.packed);
+      if (cout == 16) pack_first_conv_ts_weights(wi->second.data(), L.packed);
       if (cout == 16) {
         for (int t = 0; t < 27; ++t)
           for (int c = 0; c < 16; ++c) first_w_.w[t][c] = wi->second[(size_t)c * 27 + t];
@@ -206,7 +207,9 @@ int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPo
   {
     const ConvLayer& L = layers_.at("enc0.0");
     prof_begin("enc0.0", s);
-    if (chunk && in_dtype == CFB_DTYPE_U8 && getenv("CFB_UMMA_FIRST_CONV") && P != kFmtF16F8) launch_first_conv_umma(chunk, cs, patches, nb, s0, L.packed, h_e0a_, s);
+    if (chunk && in_dtype == CFB_DTYPE_U8 && L.packed.w_ts && !getenv("CFB_SIMT_FIRST_CONV") && !getenv("CFB_UMMA_FIRST_CONV"))
+      launch_first_conv_ts(chunk, cs, patches, nb, s0, L.packed, h_e0a_, P, s);
+    else if (chunk && in_dtype == CFB_DTYPE_U8 && getenv("CFB_UMMA_FIRST_CONV") && P != kFmtF16F8) launch_first_conv_umma(chunk, cs, patches, nb, s0, L.packed, h_e0a_, s);
     else if (chunk) launch_first_conv_cp8(chunk, in_dtype, cs, patches, nb, s0, L.w, L.bias, h_e0a_, P, s,
                                           getenv("CFB_FIRST_CONV_SMEM_W") ? nullptr : &first_w_);
     else launch_first_conv_cp8_from_patches(buf_in_, nb, s0, L.w, L.bias, h_e0a_, P, s);

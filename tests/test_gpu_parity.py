@@ -507,10 +507,11 @@ def test_kernel_variants_agree(monkeypatch, unet_model):
                            framework="pytorch", model=unet_model)
     results = {}
     for name, env in [("default", {}), ("unfused_tail", {"CFB_NO_FUSED_TAIL": "1"}), ("umma_first", {"CFB_UMMA_FIRST_CONV": "1"}),
+                      ("simt_first", {"CFB_SIMT_FIRST_CONV": "1"}),
                       ("simt_convT", {"CFB_SIMT_CONVT": "1"}), ("per_tap", {"CFB_NO_ZSTACK": "1"}), ("zstack4", {"CFB_FORCE_ZSTACK": "4"}),
                       ("no_shift", {"CFB_NO_TSHIFT": "1"}), ("shift2", {"CFB_FORCE_ZSTACK": "2", "CFB_FORCE_TSHIFT": "1"})]:
-        for k in ("CFB_NO_FUSED_TAIL", "CFB_UMMA_FIRST_CONV", "CFB_SIMT_CONVT", "CFB_NO_ZSTACK", "CFB_FORCE_ZSTACK", "CFB_NO_TSHIFT",
-                  "CFB_FORCE_TSHIFT"):
+        for k in ("CFB_NO_FUSED_TAIL", "CFB_UMMA_FIRST_CONV", "CFB_SIMT_FIRST_CONV", "CFB_SIMT_CONVT", "CFB_NO_ZSTACK", "CFB_FORCE_ZSTACK",
+                  "CFB_NO_TSHIFT", "CFB_FORCE_TSHIFT"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -530,8 +531,8 @@ def test_f16f8_unfused_and_cuda_core_paths(monkeypatch, unet_model):
     kw = dict(input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3, framework="b200", batch_size=5)
     ref, _ = O.infer_chunk(img, input_patch_size=(16, 64, 64), output_patch_overlap=(4, 16, 16), num_output_channels=3,
                            framework="pytorch", model=unet_model)
-    for env in ({}, {"CFB_NO_FUSED_TAIL": "1"}, {"CFB_SIMT_CONVT": "1"}, {"CFB_FORCE_ZSTACK": "2"}):
-        for k in ("CFB_NO_FUSED_TAIL", "CFB_SIMT_CONVT", "CFB_FORCE_ZSTACK"):
+    for env in ({}, {"CFB_NO_FUSED_TAIL": "1"}, {"CFB_SIMT_CONVT": "1"}, {"CFB_FORCE_ZSTACK": "2"}, {"CFB_SIMT_FIRST_CONV": "1"}):
+        for k in ("CFB_NO_FUSED_TAIL", "CFB_SIMT_CONVT", "CFB_FORCE_ZSTACK", "CFB_SIMT_FIRST_CONV"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)

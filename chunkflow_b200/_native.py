@@ -16,7 +16,7 @@ OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
 FRAMEWORK_UNET3L, FRAMEWORK_IDENTITY = 0, 1
 PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA, PRECISION_F16F8_UMMA = 0, 1, 2, 3
-DTYPE_U8, DTYPE_F32 = 0, 1
+DTYPE_U8, DTYPE_F32, DTYPE_U32 = 0, 1, 2
 AUGMENT_NONE, AUGMENT_REFERENCE, AUGMENT_SPATIAL = 0, 1, 2
 QUANTIZE_XY, QUANTIZE_Z = 0, 1
 
@@ -29,6 +29,7 @@ EXPORTS = (
     "cfb_patch_forward_host", "cfb_make_patch_mask", "cfb_plugin_begin", "cfb_plugin_extract", "cfb_plugin_blend",
     "cfb_plugin_end", "cfb_last_timing", "cfb_set_profiling", "cfb_layer_timing", "cfb_debug_net_forward_host", "cfb_debug_conv3_host",
     "cfb_normalize_contrast_device", "cfb_maskout_device", "cfb_crop_margin_device", "cfb_quantize_device",
+    "cfb_connected_components_device", "cfb_connected_components_workspace",
 )
 
 
@@ -111,9 +112,12 @@ def load() -> C.CDLL:
     lib.cfb_maskout_device.argtypes = [vp, i32, i64, i64, i64, i64, vp, i32, i64, i64, i64, vp]
     lib.cfb_crop_margin_device.argtypes = [vp, i32, i64, i64, i64, i64, C.POINTER(i64 * 6), vp, vp]
     lib.cfb_quantize_device.argtypes = [vp, i64, i64, i64, i64, i32, vp, vp]
+    lib.cfb_connected_components_device.argtypes = [vp, i32, i64, i64, i64, C.c_float, i32, vp, vp, C.POINTER(C.c_uint32), vp]
+    lib.cfb_connected_components_workspace.argtypes = [i64, i64, i64]
+    lib.cfb_connected_components_workspace.restype = i64
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("cfb_version", "cfb_device_count"):
+        if fn.restype is C.c_int and name not in ("cfb_version", "cfb_device_count", "cfb_connected_components_workspace"):
             fn.restype = C.c_int
     _lib = lib
     return lib
@@ -150,6 +154,20 @@ def crop_margin_device(d_src: int, dtype: int, czyx, margin6, d_dst: int, stream
 def quantize_device(d_affinity: int, czyx, mode: int, d_out: int, stream: int = 0) -> None:
     check(load().cfb_quantize_device(C.c_void_p(d_affinity), *(int(v) for v in czyx), int(mode), C.c_void_p(d_out),
                                      C.c_void_p(stream)))
+
+
+def connected_components_workspace(zyx) -> int:
+    return int(load().cfb_connected_components_workspace(*(int(v) for v in zyx)))
+
+
+def connected_components_device(d_in: int, in_dtype: int, zyx, threshold: float, connectivity: int, d_labels: int, d_workspace: int,
+                                stream: int = 0) -> int:
+    """-> number of components (synchronises the stream)."""
+    n = C.c_uint32()
+    check(load().cfb_connected_components_device(C.c_void_p(d_in), int(in_dtype), *(int(v) for v in zyx), float(threshold or 0.0),
+                                                 int(connectivity), C.c_void_p(d_labels), C.c_void_p(d_workspace), C.byref(n),
+                                                 C.c_void_p(stream)))
+    return int(n.value)
 
 
 def device_memory(device: int = 0) -> tuple:

@@ -219,6 +219,13 @@ class Chunk(NDArrayOperatorsMixin):
             src = src[1:]
         self.array[tuple(dst)] += patch.array[tuple(src)]
 
+    def connected_component(self, threshold: float = None, connectivity: int = 6) -> "Chunk":
+        """Threshold the map chunk and get connected components (reference chunk/base.py:128-137; cc3d's labelling runs as
+        CUDA kernels: the chunk is moved to the GPU and back, there is no CPU fallback)."""
+        from .device import DeviceChunk
+        dev = DeviceChunk.from_chunk(self)
+        return dev.connected_component(threshold=threshold, connectivity=connectivity).to_chunk()
+
     def mask_using_last_channel(self, threshold: float = 0.3) -> "Chunk":
         """Drop the last channel and zero where it is >= threshold (reference base.py:685-689)."""
         keep = self.array[-1] < threshold

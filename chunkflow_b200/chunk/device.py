@@ -173,5 +173,41 @@ class DeviceChunk:
             _native.quantize_device(self.tensor.data_ptr(), self.shape, code, out.data_ptr(), self._stream())
         return DeviceChunk(out, voxel_offset=self.voxel_offset, voxel_size=self.voxel_size)
 
+    # ---- Chunk.connected_component ---------------------------------------------------------
+    def connected_component(self, threshold: float = None, connectivity: int = 6) -> "DeviceChunk":
+        """Threshold the map and label its connected components (reference chunk/base.py:128-137: ``Chunk.threshold`` --
+        ``array > threshold`` -- for non-segmentation chunks, then ``cc3d.connected_components(seg, connectivity)``).
+        (z,y,x) or (1,z,y,x) float32 map with a threshold, or a uint8 / int32 / uint32 segmentation; returns a (z,y,x) uint32
+        segmentation whose components are numbered 1..N in raster order of their first voxel, like cc3d."""
+        torch = _torch()
+        t = self.tensor
+        if t.ndim == 4:
+            assert t.shape[0] == 1   # reference base.py:730-732
+            t = t[0]
+        is_seg = t.dtype in (torch.uint8, torch.bool, torch.int32, torch.uint32) or self.layer_type == "segmentation"
+        thr = 0.0
+        if not is_seg and threshold is not None:
+            assert t.dtype == torch.float32, "thresholding works on a float32 map"
+            code, thr = _native.DTYPE_F32, float(threshold)
+        elif t.dtype in (torch.uint8, torch.bool):
+            code = _native.DTYPE_U8
+        elif t.dtype in (torch.int32, torch.uint32):
+            code = _native.DTYPE_U32
+        else:
+            raise TypeError(f"connected_component: {t.dtype} without a threshold is not a segmentation (uint8 / int32 / uint32)")
+        if connectivity not in (6, 18, 26):
+            raise ValueError("connectivity must be 6, 18 or 26")
+        t = t.contiguous()
+        labels = torch.empty(t.shape, dtype=torch.int32, device=t.device)   # uint32 values (torch has no full uint32 support)
+        work = torch.empty(_native.connected_components_workspace(t.shape), dtype=torch.uint8, device=t.device)
+        with self._on_device():
+            self.num_components = _native.connected_components_device(t.data_ptr(), code, tuple(t.shape), thr, connectivity,
+                                                                      labels.data_ptr(), work.data_ptr(), self._stream())
+        del work
+        out = DeviceChunk(labels.view(torch.uint32) if hasattr(torch, "uint32") else labels, voxel_offset=self.voxel_offset,
+                          voxel_size=self.voxel_size, layer_type="segmentation")
+        out.num_components = self.num_components
+        return out
+
     def __repr__(self):
         return f"DeviceChunk(shape={self.shape}, dtype={self.dtype}, voxel_offset={tuple(self.voxel_offset)}, device={self.tensor.device})"

@@ -1,0 +1,244 @@
+// `connected-components` on the device: the operator that follows `inference` in the reference's
+// README pipeline.  Reference: Chunk.connected_component (chunkflow/chunk/base.py:128-137) -> Chunk.threshold (:728-737) ->
+// cc3d.connected_components(seg, connectivity) -- cc3d is a third-party package that is NOT vendored in the reference tree
+// (requirements.txt: connected-components-3d); its published behaviour, restated in oracle/segmentation_oracle.py:
+//   * voxels are connected when they are 6 / 18 / 26-neighbours AND carry the same non-zero value (multi-label input),
+//   * 0 is background and stays 0,
+//   * output labels are 1 .. N, numbered in the order in which the components are first met in a raster scan of the
+//     memory (x fastest, then y, then z for a C-order (z, y, x) array).
+//
+// Kernels (HBM / atomic bound, no tensor work): label-equivalence union-find over the voxels' linear indices
+//   init      P[i] = i
+//   merge     for every foreground voxel, unite with the backward half of its neighbourhood (3 / 9 / 13 neighbours)
+//             that carries the same value: root search + atomicMin on the larger root (lock-free, any order)
+//   flatten   P[i] = root(i): the root of a component is its smallest linear index = its first voxel in raster order
+//   rank      exclusive prefix sum of the root flags in raster order (two-level scan) -> label of a root = rank + 1
+//   relabel   out[i] = rank[P[i]] + 1 for foreground, 0 for background
+#include <algorithm>
+#include <cstdint>
+#include <stdexcept>
+#include <type_traits>
+
+#include "chunkflow_b200.h"
+#include "common.cuh"
+
+namespace cfb {
+namespace {
+
+constexpr int kT = 256;
+constexpr int kScanBlock = 4096;  // voxels per scan block (16 per thread)
+
+template <typename T>
+__device__ __forceinline__ uint32_t fg_value(const T* __restrict__ in, int64_t i, float threshold, bool use_threshold) {
+  if constexpr (sizeof(T) == 4 && !std::is_integral<T>::value) {
+    return in[i] > threshold ? 1u : 0u;  // Chunk.threshold: array > threshold (base.py:729)
+  } else {
+    (void)threshold; (void)use_threshold;
+    return (uint32_t)in[i];
+  }
+}
+
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* P, uint32_t x) {
+  uint32_t p = P[x];
+  while (p != x) { x = p; p = P[x]; }
+  return x;
+}
+
+__device__ __forceinline__ void uf_unite(uint32_t* P, uint32_t a, uint32_t b) {
+  bool done = false;
+  do {
+    a = uf_find(P, a);
+    b = uf_find(P, b);
+    if (a < b) {
+      const uint32_t old = atomicMin(&P[b], a);
+      done = old == b;
+      b = old;
+    } else if (b < a) {
+      const uint32_t old = atomicMin(&P[a], b);
+      done = old == a;
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kT) cc_init_kernel(const T* __restrict__ in, uint32_t* __restrict__ P, uint32_t* __restrict__ val,
+                                                     int64_t n, float threshold) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    P[i] = (uint32_t)i;
+    val[i] = fg_value(in, i, threshold, true);
+  }
+}
+
+// backward half of the 26-neighbourhood, ordered so that the first 3 are the face neighbours (6-connectivity), the first 9
+// the face + edge neighbours (18) and all 13 the full neighbourhood (26)
+__constant__ int kNb[13][3] = {{0, 0, -1}, {0, -1, 0}, {-1, 0, 0},
+                               {0, -1, -1}, {0, -1, 1}, {-1, 0, -1}, {-1, 0, 1}, {-1, -1, 0}, {-1, 1, 0},
+                               {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1}};
+
+__global__ void __launch_bounds__(kT) cc_merge_kernel(const uint32_t* __restrict__ val, uint32_t* __restrict__ P, Int3 sz, int nnb) {
+  const int64_t n = (int64_t)sz.z * sz.y * sz.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = val[i];
+    if (!v) continue;
+    const int x = (int)(i % sz.x), y = (int)((i / sz.x) % sz.y), z = (int)(i / ((int64_t)sz.x * sz.y));
+    for (int k = 0; k < nnb; ++k) {
+      const int zz = z + kNb[k][0], yy = y + kNb[k][1], xx = x + kNb[k][2];
+      if (zz < 0 || yy < 0 || yy >= sz.y || xx < 0 || xx >= sz.x) continue;
+      const int64_t j = ((int64_t)zz * sz.y + yy) * sz.x + xx;
+      if (val[j] == v) uf_unite(P, (uint32_t)i, (uint32_t)j);
+    }
+  }
+}
+
+// flatten + per-block count of roots
+__global__ void __launch_bounds__(kT) cc_flatten_count_kernel(const uint32_t* __restrict__ val, uint32_t* __restrict__ P, int64_t n,
+                                                              uint32_t* __restrict__ block_count) {
+  __shared__ uint32_t s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock;
+  uint32_t mine = 0;
+  for (int k = 0; k < kScanBlock / kT; ++k) {
+    const int64_t i = base + k * kT + threadIdx.x;
+    if (i < n && val[i]) {
+      const uint32_t r = uf_find(P, (uint32_t)i);
+      P[i] = r;   // (roots keep P[r] == r; concurrent readers only ever see an ancestor)
+      mine += r == (uint32_t)i;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_count, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) block_count[blockIdx.x] = s_count;
+}
+
+// exclusive scan of the block counts by ONE block (sequential chunks of 1024 with a carry), total -> *num_labels
+__global__ void __launch_bounds__(1024) cc_scan_blocks_kernel(uint32_t* __restrict__ block_count, int64_t nblocks, uint32_t* __restrict__ num_labels) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < nblocks; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = i < nblocks ? block_count[i] : 0u;
+    uint32_t incl = v;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_warp[lane];
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t before = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - v;
+    if (i < nblocks) block_count[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *num_labels = s_carry;
+}
+
+// rank of every root inside its block (raster order) + the block's base -> rank[root]
+__global__ void __launch_bounds__(kT) cc_rank_kernel(const uint32_t* __restrict__ val, const uint32_t* __restrict__ P, int64_t n,
+                                                     const uint32_t* __restrict__ block_base, uint32_t* __restrict__ rank) {
+  __shared__ uint32_t s_warp[kT / 32];
+  __shared__ uint32_t s_running;
+  if (threadIdx.x == 0) s_running = block_base[blockIdx.x];
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kScanBlock;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < kScanBlock / kT; ++k) {   // chunk k holds 256 CONSECUTIVE voxels: raster order is preserved
+    const int64_t i = base + k * kT + threadIdx.x;
+    const bool root = i < n && val[i] && P[i] == (uint32_t)i;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, root);
+    const uint32_t in_warp = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = s_running;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (root) rank[i] = before + in_warp;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < kT / 32; ++w) t += s_warp[w]; s_running += t; }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kT) cc_relabel_kernel(const uint32_t* __restrict__ val, const uint32_t* __restrict__ P,
+                                                        const uint32_t* __restrict__ rank, uint32_t* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = val[i] ? rank[P[i]] + 1u : 0u;
+}
+
+int grid_for(int64_t items) {
+  int64_t b = ceil_div64(items, kT);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(b, 148 * 16));
+}
+
+}  // namespace
+}  // namespace cfb
+
+using namespace cfb;
+
+extern "C" int cfb_connected_components_device(const void* d_in, int32_t in_dtype, int64_t z, int64_t y, int64_t x, float threshold,
+                                               int32_t connectivity, uint32_t* d_labels, void* d_workspace, uint32_t* num_labels,
+                                               void* stream) {
+  try {
+    if (!d_in || !d_labels || !d_workspace) throw std::invalid_argument("null argument");
+    if (z <= 0 || y <= 0 || x <= 0 || z > INT32_MAX || y > INT32_MAX || x > INT32_MAX) throw std::invalid_argument("bad volume size");
+    const int64_t n = z * y * x;
+    if (n >= (int64_t)UINT32_MAX) throw std::invalid_argument("connected components: more than 2^32 - 1 voxels");
+    int nnb;
+    if (connectivity == 6) nnb = 3; else if (connectivity == 18) nnb = 9; else if (connectivity == 26) nnb = 13;
+    else throw std::invalid_argument("connectivity must be 6, 18 or 26 (cc3d)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const Int3 sz{(int)z, (int)y, (int)x};
+    // workspace: P (n) | val (n) | rank (n, written at root positions only) | block counts (ceil(n / 4096)) | label count (1)
+    uint32_t* P = static_cast<uint32_t*>(d_workspace);
+    uint32_t* val = P + n;
+    uint32_t* rank = val + n;
+    const int64_t nblocks = ceil_div64(n, kScanBlock);
+    uint32_t* block_count = rank + n;
+    uint32_t* d_num = block_count + nblocks;
+    if (in_dtype == CFB_DTYPE_U8) cc_init_kernel<uint8_t><<<grid_for(n), kT, 0, s>>>((const uint8_t*)d_in, P, val, n, 0.f);
+    else if (in_dtype == CFB_DTYPE_U32) cc_init_kernel<uint32_t><<<grid_for(n), kT, 0, s>>>((const uint32_t*)d_in, P, val, n, 0.f);
+    else if (in_dtype == CFB_DTYPE_F32) cc_init_kernel<float><<<grid_for(n), kT, 0, s>>>((const float*)d_in, P, val, n, threshold);
+    else throw std::invalid_argument("connected components: input dtype must be uint8, uint32 or float32 (with a threshold)");
+    CFB_LAUNCH_CHECK();
+    cc_merge_kernel<<<grid_for(n), kT, 0, s>>>(val, P, sz, nnb);
+    CFB_LAUNCH_CHECK();
+    cc_flatten_count_kernel<<<(unsigned)nblocks, kT, 0, s>>>(val, P, n, block_count);
+    CFB_LAUNCH_CHECK();
+    cc_scan_blocks_kernel<<<1, 1024, 0, s>>>(block_count, nblocks, d_num);
+    CFB_LAUNCH_CHECK();
+    cc_rank_kernel<<<(unsigned)nblocks, kT, 0, s>>>(val, P, n, block_count, rank);
+    CFB_LAUNCH_CHECK();
+    cc_relabel_kernel<<<grid_for(n), kT, 0, s>>>(val, P, rank, d_labels, n);
+    CFB_LAUNCH_CHECK();
+    if (num_labels) {
+      CFB_CUDA(cudaMemcpyAsync(num_labels, d_num, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CFB_CUDA(cudaStreamSynchronize(s));
+    }
+    return CFB_OK;
+  } catch (const std::invalid_argument& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_INVALID_ARGUMENT;
+  } catch (const CudaError& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_CUDA;
+  } catch (const std::exception& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int64_t cfb_connected_components_workspace(int64_t z, int64_t y, int64_t x) {
+  if (z <= 0 || y <= 0 || x <= 0) return 0;
+  const int64_t n = z * y * x;
+  return (3 * n + ceil_div64(n, kScanBlock) + 1) * (int64_t)sizeof(uint32_t);
+}

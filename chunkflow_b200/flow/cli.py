@@ -251,5 +251,28 @@ def quantize(tasks, input_chunk_name, output_chunk_name, mode):
         yield task
 
 
+@main.command("connected-components")
+@click.option("--name", type=str, default="connected-components", help="threshold a map and get the targets.")
+@click.option("--input-chunk-name", "-i", type=str, default="chunk", help="input chunk name")
+@click.option("--output-chunk-name", "-o", type=str, default="chunk", help="output chunk name")
+@click.option("--threshold", "-t", type=click.FLOAT, default=None, help="threshold to cut the map.")
+@click.option("--connectivity", "-c", type=click.Choice(["6", "18", "26"]), default="6",
+              help="number of neighboring voxels used. Default is 6.")
+@operator
+def connected_components(tasks, name, input_chunk_name, output_chunk_name, threshold, connectivity):
+    """Threshold the probability map to get a segmentation (reference flow/flow.py:1803-1830, chunk/base.py:128-137)."""
+    import torch
+    connectivity = int(connectivity)
+    for task in tasks:
+        if task is not None:
+            start = time()
+            dev, was_host = _on_device(task[input_chunk_name], "cuda:0")
+            out = dev.connected_component(threshold=threshold, connectivity=connectivity)
+            torch.cuda.synchronize(out.tensor.device)
+            task[output_chunk_name] = out.to_chunk() if was_host else out
+            task["log"]["timer"][name] = time() - start
+        yield task
+
+
 if __name__ == "__main__":
     main()

@@ -69,6 +69,7 @@ extern "C" {
 /* dtype of the input chunk */
 #define CFB_DTYPE_U8 0
 #define CFB_DTYPE_F32 1
+#define CFB_DTYPE_U32 2 /* connected components on an integer segmentation */
 
 typedef struct cfb_engine* cfb_handle;
 
@@ -236,6 +237,17 @@ int cfb_crop_margin_device(const void* d_src, int32_t dtype, int64_t channels, i
  * arithmetic, C truncation. */
 int cfb_quantize_device(const float* d_affinity, int64_t channels, int64_t z, int64_t y, int64_t x, int32_t mode,
                         uint8_t* d_out, void* stream);
+
+/* `connected-components`: Chunk.connected_component (reference chunk/base.py:128-137) =
+ * [Chunk.threshold: array > threshold (:728-737)] + cc3d.connected_components(seg, connectivity).  d_in: (z,y,x) uint8 / uint32
+ * labels (0 = background; equal non-zero values connect) or float32 (thresholded first); connectivity 6 / 18 / 26;
+ * d_labels: (z,y,x) uint32, components numbered 1..N in the order of their first voxel in a raster scan (x fastest), like cc3d.
+ * d_workspace: cfb_connected_components_workspace(z,y,x) bytes of device memory.  num_labels (host, may be NULL; when given the
+ * stream is synchronised) receives N. */
+int cfb_connected_components_device(const void* d_in, int32_t in_dtype, int64_t z, int64_t y, int64_t x, float threshold,
+                                    int32_t connectivity, uint32_t* d_labels, void* d_workspace, uint32_t* num_labels,
+                                    void* stream);
+int64_t cfb_connected_components_workspace(int64_t z, int64_t y, int64_t x);
 
 #ifdef __cplusplus
 }

@@ -353,6 +353,7 @@ struct UmmaConvParams {
 constexpr int kRing = 3;       // z-plane ring slots
 constexpr int kMaxBStages = 64; // weight block stages: resident (27 * KG <= 54 blocks) or a ring of up to 64
 constexpr int kThreads = 224;  // 7 warps
+constexpr int kThreadsConvT = 352;  // transposed convolution: 4 more epilogue warps
 constexpr int kTailPad = 2304; // dense M tiles may read up to 129 voxel records past the last plane
 constexpr int kBufCols = 256;  // TMEM columns per accumulator buffer (2 buffers)
 constexpr int kBarBytes = (10 + 2 * 64) * 8 + 16 + 640;  // mbarriers + TMEM base slot + head weights (fused tail)
@@ -1273,7 +1274,7 @@ struct UmmaConvTParams {
 };
 
 template <int CIN, int COUT, bool SPLIT, bool F8 = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsConvT, 1)
 convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParams p) {
   constexpr int P = SPLIT ? 2 : 1;
   constexpr int NPL = P * CIN / 8;
@@ -1297,7 +1298,7 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 3; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(8 + i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(8 + i), 256); }  // two sets of four epilogue warps
     mbar_init(BAR(10), 1);
     fence_barrier_init();
     fence_proxy_async();
@@ -1372,7 +1373,9 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
       }
     }
   } else {
-    const int wq = warp & 3;
+    // epilogue (warps 3..6 = set 0, 7..10 = set 1): the scatter of the four taps is a chain of tcgen05.ld, encode and
+    // 16-byte stores per tap -- the two warps of a lane quarter take two taps each
+    const int wq = warp & 3, eset = warp >= 7 ? 1 : 0;
     const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
     const int OY = 2 * p.Y, OX = 2 * p.X;
     const size_t oplane_vox = (size_t)p.Z * OY * OX;
@@ -1390,6 +1393,7 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kBufCols + g * N1);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+          if ((t & 1) != eset) continue;
           const size_t ovox = ((size_t)z * OY + (2 * (y0 + row) + (t >> 1))) * OX + (2 * (x0 + col) + (t & 1));
 #pragma unroll
           for (int cb = 0; cb < COUT / 16; ++cb) {
@@ -1983,7 +1987,7 @@ void launch_convT_cfg(const __half* in, const PackedConv& w, __half* out, int nb
   const CUtensorMap mapA = make_map(in, nb * p.planes * P, sz, p.XT, p.TY, p.planes * P, /*wide=*/false);
   auto kern = convT_umma_kernel<CIN, COUT, SPLIT, F8>;
   CFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<nb * p.tiles_x * p.tiles_y, kThreads, smem, s>>>(mapA, p);
+  kern<<<nb * p.tiles_x * p.tiles_y, kThreadsConvT, smem, s>>>(mapA, p);
   CFB_LAUNCH_CHECK();
 }
 

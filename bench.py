@@ -401,7 +401,8 @@ def main():
     achieved = dom_flop_per_launch / (dom_ms / dom_launches / 1e3) / 1e12 if dom_ms > 0 else 0.0
     traffic, pipe_note = None, ""
     try:  # DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_ncu_traffic.json), scaled to this batch
-        tl = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["layers"]
+        prof = "r02_ncu_traffic.json" if eng.params.precision == 3 else "r01_ncu_traffic.json"   # --set full capture of the same precision mode
+        tl = json.load(open(os.path.join(ROOT, "profiles", prof)))["layers"]
         t = tl.get(dom)
         if t and t.get("dram_bytes_per_patch"):
             traffic = t["dram_bytes_per_patch"] * P / dom_launches
@@ -418,7 +419,7 @@ def main():
                 "algorithmic_flop_per_launch": dom_flop_per_launch,
                 "note": ("the f16f8 mode executes 2x these algorithmic FLOPs on the tensor pipe (one fp16 + one e4m3 K=32 product per multiply)"
                          if eng.params.precision == 3 else "the fp16 hi/lo split (f16x3) executes 3x these algorithmic FLOPs on the tensor pipe") + pipe_note +
-                        " (profiles/r01_ncu_full_summary.md)",
+                        " (profiles/r02_ncu_full_summary.md / r01_ncu_full_summary.md)",
                 "conv_stack": {"achieved": conv_flop / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0, "unit": "TFLOP/s",
                                "ms_per_chunk": conv_ms, "launches": conv_launches, "algorithmic_flop_per_chunk": conv_flop}}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -531,6 +532,7 @@ def main():
     # ---- BASELINE config #5: ONE 512x2048x2048 chunk split over the N ranks, halo planes exchanged over NCCL
     split = None
     if world > 1 and not args.no_split_chunk:
+        inf._last_result = None   # the recycled 12.9 GB host result of the pageable block
         del d_out
         torch.cuda.empty_cache()
         split = split_chunk_block(inf, Chunk, patch, overlap, rank, world, local_rank, args, barrier, max_over_ranks)

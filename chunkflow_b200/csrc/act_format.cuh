@@ -62,18 +62,23 @@ __device__ __forceinline__ void af_unpack_e4m3x4(uint32_t u, float (&v)[4]) {
   v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
 }
 
-// 16 channels of one voxel (one K step) -> the four 16-byte records (H 0..7, H 8..15, A8 0..15, L8 0..15)
+// 16 channels of one voxel (one K step) -> the four 16-byte records (H 0..7, H 8..15, A8 0..15, L8 0..15).
+// Per channel pair: one packed f16x2 conversion, its two widenings, and the residual as ONE fma each
+// (L * lambda = a * (alpha lambda) - H * lambda, exact: the products are power-of-two scalings).
 __device__ __forceinline__ void af_encode16(const float (&v)[16], uint4& h0, uint4& h1, uint4& a8, uint4& l8) {
-  float s[16], l[16];
+  uint32_t hw[8];
+  float l[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    s[i] = fminf(fmaxf(v[i] * kActAlpha, -kHalfMax), kHalfMax);
-    const float h = __half2float(__float2half_rn(s[i]));
-    l[i] = (s[i] - h) * kActLambda;
-    s[i] = h;
+  for (int i = 0; i < 8; ++i) {
+    const float s0 = fminf(fmaxf(v[2 * i] * kActAlpha, -kHalfMax), kHalfMax), s1 = fminf(fmaxf(v[2 * i + 1] * kActAlpha, -kHalfMax), kHalfMax);
+    const __half2 h = __floats2half2_rn(s0, s1);
+    const float2 f = __half22float2(h);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&h);
+    l[2 * i] = fmaf(f.x, -kActLambda, s0 * kActLambda);
+    l[2 * i + 1] = fmaf(f.y, -kActLambda, s1 * kActLambda);
   }
-  h0 = make_uint4(af_pack_half2(s[0], s[1]), af_pack_half2(s[2], s[3]), af_pack_half2(s[4], s[5]), af_pack_half2(s[6], s[7]));
-  h1 = make_uint4(af_pack_half2(s[8], s[9]), af_pack_half2(s[10], s[11]), af_pack_half2(s[12], s[13]), af_pack_half2(s[14], s[15]));
+  h0 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  h1 = make_uint4(hw[4], hw[5], hw[6], hw[7]);
   a8 = make_uint4(af_pack_e4m3x4(v[0] * kActGamma, v[1] * kActGamma, v[2] * kActGamma, v[3] * kActGamma),
                   af_pack_e4m3x4(v[4] * kActGamma, v[5] * kActGamma, v[6] * kActGamma, v[7] * kActGamma),
                   af_pack_e4m3x4(v[8] * kActGamma, v[9] * kActGamma, v[10] * kActGamma, v[11] * kActGamma),

@@ -345,6 +345,7 @@ struct UmmaConvParams {
   int niss;        // TMEM-shift kernel: MMA-issuing threads (1..4; M tiles are dealt round-robin so every accumulator has ONE issuer)
   int ring;        // TMEM-shift kernel: z-plane slots in shared memory (2 or 3)
   int ngroups;     // TMEM-shift kernel: depth of the ring of A-tile groups in tensor memory (2..4)
+  __half* out_pool;  // TMEM-shift kernel, POOL instantiations: (1,2,2) max-pooled copy of the output (CP8, half the y / x extent)
   int ablate;      // CFB_TS_ABLATE builds only: 1 no global stores, 2 no epilogue TMEM reads, 4 no loader copies,
                    // 8 no shifts, 16 no MMAs, 32 no TMA plane loads
   long long* trace;  // CFB_TS_TRACE builds only: 16 cycle counters per CTA
@@ -886,7 +887,7 @@ constexpr int kTsACol0 = 384;     // groups live at columns [384, 512)
 constexpr int kTsAccCols = 192;   // accumulator columns per buffer (2 buffers)
 constexpr int kTsBarBytes = (10 + 2 * 64 + 2 * kTsGroups) * 8 + 16 + 640;
 
-template <int CIN, int COUT, bool SPLIT, bool TAIL, bool F8 = false>
+template <int CIN, int COUT, bool SPLIT, bool TAIL, bool F8 = false, bool POOL = false>
 __global__ void __launch_bounds__(TAIL ? kThreadsTSTail : kThreadsTS, 1)
 conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                      const UmmaConvParams p) {
@@ -922,6 +923,8 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   constexpr int kTF = 10 + 2 * kMaxBStages, kTE = kTF + kTsGroups;  // TMEM A-tile group full / empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTE + kTsGroups);
   float* s_head = reinterpret_cast<float*>(bars + kTE + kTsGroups + 2);
+  // POOL: staging buffer [TY][XT / 2][16] fp32 of the x-pooled values of one (plane, 16-channel block), behind the barrier area
+  [[maybe_unused]] float4* s_pool = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + kTsBarBytes);
   PatchPos pp{};
   if constexpr (TAIL) {
     for (int i = threadIdx.x; i < p.tail.channels * 16; i += blockDim.x) s_head[i] = p.tail.head_w[i];
@@ -1195,6 +1198,76 @@ conv3_ts_umma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       if constexpr (TAIL) pp = p.tail.patches[b];
       CFB_TRACE_WAIT(tr_accf, mbar_wait(BAR(kAccF + buf), (uint32_t)(jj >> 1) & 1u));
       tc_fence_after();
+      if constexpr (POOL) {
+        // Fused (1,2,2) max pooling (the layer's output is both a skip connection and, pooled, the next level's input): per
+        // (plane, 16-channel block) every thread stores its full-resolution voxel, takes the max with its x neighbour (the
+        // adjacent lane: tile bases, pitch and x0 are even) and the even lane parks the pair in shared memory; the y partner of a
+        // row lives in another warp's lane quarter or in the next M tile, so after a barrier of the four epilogue warps thread t
+        // finishes pooled voxel t from two staged rows, encodes and stores it.
+        const int hx = p.XT >> 1;
+        const int npool = (p.TY >> 1) * hx;
+        const size_t pool_plane_vox = (size_t)p.Z * (p.Y >> 1) * (p.X >> 1);
+        uint4* pool16 = reinterpret_cast<uint4*>(p.out_pool);
+        const int tid = (warp - 3) * 32 + lane;   // 0..127 over the epilogue warps 3..6
+        for (int pz = z0; pz < z1; ++pz) {
+#pragma unroll
+          for (int cb = 0; cb < COUT / 16; ++cb) {
+            for (int g = 0; g < p.G; ++g) {
+              const int qpos = g * 120 + 30 * wq + lane;
+              const int row = __float2int_rd(((float)qpos + 0.5f) * inv_pitch), col = qpos - row * p.pitch;
+              const bool valid = lane < 30 && row < ty_valid && col < xt_valid;
+              const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * kTsAccCols + (g * T + (pz - z0)) * COUT) + cb * 16;
+              uint32_t r[16];
+              tc_ld16(taddr, r);
+              float v[16];
+              tc_wait_ld();
+              {
+                const uint32_t zero[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+                tc_st16(taddr, zero);   // clear the accumulator columns for their next use
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                v[i] = __uint_as_float(r[i]);
+                if constexpr (F8) v[i] *= p.acc_scale;
+                v[i] += __ldg(p.bias + cb * 16 + i);
+                if (p.relu) v[i] = relu_nan(v[i]);
+              }
+              if (valid) {
+                const size_t vox = ((size_t)pz * p.Y + (y0 + row)) * p.X + (x0 + col);
+                if constexpr (F8) store_cp8_16_f8<COUT>(v, cb, b, vox, plane_vox, out16);
+                else store_cp8_16<COUT, SPLIT>(v, cb, b, vox, plane_vox, out16);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+              if (valid && !(lane & 1)) {
+                float4* dst = s_pool + ((size_t)row * hx + (col >> 1)) * 4;
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+                dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+              }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps: every row of the plane is staged
+            for (int t = tid; t < npool; t += 128) {
+              const int pr = t / hx, pc = t - pr * hx;
+              if (2 * pr < ty_valid && 2 * pc < xt_valid) {
+                const float4* a = s_pool + ((size_t)(2 * pr) * hx + pc) * 4;
+                const float4* c = s_pool + ((size_t)(2 * pr + 1) * hx + pc) * 4;
+                float m[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 u = a[q], w = c[q];
+                  m[4 * q] = fmaxf(u.x, w.x); m[4 * q + 1] = fmaxf(u.y, w.y); m[4 * q + 2] = fmaxf(u.z, w.z); m[4 * q + 3] = fmaxf(u.w, w.w);
+                }
+                const size_t pvox = ((size_t)pz * (p.Y >> 1) + ((y0 >> 1) + pr)) * (p.X >> 1) + ((x0 >> 1) + pc);
+                if constexpr (F8) store_cp8_16_f8<COUT>(m, cb, b, pvox, pool_plane_vox, pool16);
+                else store_cp8_16<COUT, SPLIT>(m, cb, b, pvox, pool_plane_vox, pool16);
+              }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // staged rows are consumed: the buffer may be rewritten
+          }
+        }
+      } else
       for (int g = 0; g < p.G; ++g) {
         const int qpos = g * 120 + 30 * wq + lane;
         const int row = __float2int_rd(((float)qpos + 0.5f) * inv_pitch), col = qpos - row * p.pitch;
@@ -1672,7 +1745,7 @@ constexpr int kMaxSmem = 232448;  // 227 KB
 //   (halo amplification of the z-plane loads)/2 + (M-tile positions per useful output), scaled by
 //   the wave quantisation of the grid, + a penalty for shallow weight rings.
 template <int CIN, int COUT, bool SPLIT>
-std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count, bool ts_only = false) {
+std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count, bool ts_only = false, bool pool = false) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
   std::vector<ConvTile> out;
   const int ty_cap = std::min(16, (sz.y + 1) & ~1);
@@ -1755,7 +1828,7 @@ std::vector<ConvTile> enumerate_tiles(int nb, Int3 sz, int sm_count, bool ts_onl
           const size_t slot = (Cfg::NPL * plane + 127) / 128 * 128;
           const int G = ceil_div(tyc * pitch, 120);
           if (G * T * COUT > kTsAccCols || Cfg::P * G > kTsMaxTiles || slot >= (1u << 18)) continue;
-          const size_t fixed = (size_t)kTsBarBytes + kTailPad + 128;
+          const size_t fixed = (size_t)kTsBarBytes + kTailPad + 128 + (pool ? (size_t)tyc * (XT / 2) * 64 : 0);  // + pooling staging buffer
           for (int ring = 3; ring >= 2; --ring) {
           // two plane slots are enough in steady state (the loaders free a slot as soon as its copies are in tensor memory)
           // and leave room for larger tiles / resident weights on the wide layers
@@ -1802,7 +1875,7 @@ int sm_count();
 
 template <int CIN, int COUT, bool SPLIT, bool F8 = false>
 void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w,
-                 __half* out, int nb, Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail = nullptr) {
+                 __half* out, int nb, Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail = nullptr, __half* pool_out = nullptr) {
   using Cfg = ConvCfg<CIN, COUT, SPLIT>;
   UmmaConvParams p{};
   p.Z = sz.z; p.Y = sz.y; p.X = sz.x;
@@ -1840,7 +1913,9 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
   }
   const size_t bstage = t.shift ? 9 * (size_t)Cfg::BSTAGE : (t.T ? 3 * (size_t)Cfg::BSTAGE : (size_t)Cfg::BSTAGE);
   p.ring = t.shift ? t.ring : kRing;
-  const size_t smem = (size_t)p.ring * p.slot_stride + (size_t)p.bstages * bstage + (t.shift ? kTsBarBytes : kBarBytes) + kTailPad + 128;
+  p.out_pool = pool_out;
+  const size_t pool_bytes = (pool_out && t.shift) ? (size_t)p.TY * (p.XT / 2) * 64 : 0;
+  const size_t smem = (size_t)p.ring * p.slot_stride + (size_t)p.bstages * bstage + (t.shift ? kTsBarBytes : kBarBytes) + kTailPad + 128 + pool_bytes;
   const CUtensorMap mapA = make_map(srcA, nb * p.planes_a * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_a * Cfg::P, t.wide);
   const CUtensorMap mapB = cb > 0 ? make_map(srcB, nb * p.planes_b * Cfg::P, sz, p.pitch, p.TY + 2, p.planes_b * Cfg::P, t.wide) : mapA;
   int grid = nb * p.tiles_x * p.tiles_y;
@@ -1879,9 +1954,18 @@ void launch_tile(const ConvTile& t, const __half* srcA, int ca, const __half* sr
     }
   }
   if (t.shift) {
+    if (pool_out) {  // (1,2,2) max pooling fused into the epilogue (the two encoder layers that feed a pool)
+      if constexpr ((CIN == 16 && COUT == 16) || (CIN == 32 && COUT == 32)) run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false, F8, true>, kThreadsTS);
+      else throw std::runtime_error("fused pooling exists for the 16->16 and 32->32 layers");
+      return;
+    }
     run(conv3_ts_umma_kernel<CIN, COUT, SPLIT, false, F8>, kThreadsTS);
     return;
   }
+  struct PoolAfter {  // the other kernel variants pool with the stand-alone kernel
+    __half* out; __half* pool; int cout, fmt, nb; Int3 sz; cudaStream_t s;
+    ~PoolAfter() noexcept(false) { if (pool && !std::uncaught_exceptions()) launch_maxpool_cp8(out, pool, cout, fmt, nb, sz, s); }
+  } pool_after{out, pool_out, COUT, w.fmt ? w.fmt : (SPLIT ? kFmtF16x2 : kFmtF16), nb, sz, s};
   if (t.T) {
     if constexpr (3 * Cfg::NB <= 256) {
       run(conv3_zs_umma_kernel<CIN, COUT, SPLIT, false>);
@@ -1907,11 +1991,11 @@ int sm_count() {
 // tiling computes bit-identical results) and cache the winner in the layer's PackedConv.
 template <int CIN, int COUT, bool SPLIT, bool F8 = false>
 void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
-                Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail) {
+                Int3 sz, bool relu, cudaStream_t s, const FusedTail* tail, __half* pool_out = nullptr) {
   const uint64_t key = ((uint64_t)sz.z << 48) ^ ((uint64_t)sz.y << 32) ^ ((uint64_t)sz.x << 16) ^ (uint64_t)nb;
   auto it = w.tuned->find(key);
   if (it == w.tuned->end()) {
-    std::vector<ConvTile> cands = enumerate_tiles<CIN, COUT, SPLIT>(nb, sz, sm_count(), F8);
+    std::vector<ConvTile> cands = enumerate_tiles<CIN, COUT, SPLIT>(nb, sz, sm_count(), F8, pool_out != nullptr);
     if (cands.empty()) throw std::runtime_error("conv3_umma: no tile configuration fits shared memory / TMEM");
     ConvTile best = cands[0];
     const int64_t work = (int64_t)nb * vol(sz);
@@ -1936,11 +2020,11 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
       cands.swap(pick);
       const size_t n = cands.size();
       for (size_t i = 0; i < n; ++i) {
-        launch_tile<CIN, COUT, SPLIT, F8>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);  // warm
+        launch_tile<CIN, COUT, SPLIT, F8>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s, nullptr, pool_out);  // warm
         float ms = 1e30f;
         for (int rep = 0; rep < 2; ++rep) {  // best of two: one sample per candidate picked a 5-10 % slower tiling now and then
           CFB_CUDA(cudaEventRecord(e0, s));
-          launch_tile<CIN, COUT, SPLIT, F8>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s);
+          launch_tile<CIN, COUT, SPLIT, F8>(cands[i], srcA, ca, srcB, cb, w, out, nb, sz, relu, s, nullptr, pool_out);
           CFB_CUDA(cudaEventRecord(e1, s));
           CFB_CUDA(cudaEventSynchronize(e1));
           float t = 0.f;
@@ -1966,7 +2050,7 @@ void launch_cfg(const __half* srcA, int ca, const __half* srcB, int cb, const Pa
 #ifdef CFB_TS_TRACE
   g_trace_print = getenv("CFB_TS_TRACE_PRINT") != nullptr;
 #endif
-  launch_tile<CIN, COUT, SPLIT, F8>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
+  launch_tile<CIN, COUT, SPLIT, F8>(it->second, srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail, pool_out);
 #ifdef CFB_TS_TRACE
   g_trace_print = false;
 #endif
@@ -2006,10 +2090,10 @@ void launch_convT_cfg(const __half* in, const PackedConv& w, __half* out, int nb
 
 template <bool SPLIT, bool F8 = false>
 void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb, Int3 sz,
-              bool relu, cudaStream_t s, const FusedTail* tail) {
+              bool relu, cudaStream_t s, const FusedTail* tail, __half* pool_out) {
   const int cin = ca + cb, cout = w.cout;
 #define CFB_CASE(CI, CO) \
-  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT, F8>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail);
+  if (cin == CI && cout == CO) return launch_cfg<CI, CO, SPLIT, F8>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail, pool_out);
   CFB_CASE(16, 16) CFB_CASE(16, 32) CFB_CASE(32, 32) CFB_CASE(32, 64) CFB_CASE(64, 64) CFB_CASE(64, 32) CFB_CASE(32, 16)
 #undef CFB_CASE
   throw std::runtime_error("conv3_umma: unsupported channel configuration " + std::to_string(cin) + "->" + std::to_string(cout));
@@ -2018,7 +2102,8 @@ void dispatch(const __half* srcA, int ca, const __half* srcB, int cb, const Pack
 }  // namespace
 
 void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out, int nb,
-                       Int3 sz, bool relu, cudaStream_t s, const ConvTail* tail) {
+                       Int3 sz, bool relu, cudaStream_t s, const ConvTail* tail, __half* pool_out) {
+  if (pool_out && (tail || (sz.y & 1) || (sz.x & 1))) throw std::runtime_error("conv3_umma: fused pooling needs even y, x and no fused tail");
   if (ca % 16 || (cb % 16) || w.cin != ca + cb) throw std::runtime_error("conv3_umma: channel mismatch");
   FusedTail ft{};
   if (tail) {
@@ -2027,9 +2112,9 @@ void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, c
     ft.channels = tail->channels; ft.op = tail->out_patch; ft.crop = tail->crop; ft.os = tail->out_size;
     ft.scale = tail->scale;
   }
-  if (w.fmt == kFmtF16F8) dispatch<true, true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
-  else if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
-  else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr);
+  if (w.fmt == kFmtF16F8) dispatch<true, true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr, pool_out);
+  else if (w.parts == 2) dispatch<true>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr, pool_out);
+  else dispatch<false>(srcA, ca, srcB, cb, w, out, nb, sz, relu, s, tail ? &ft : nullptr, pool_out);
 }
 
 // ------------------------------------------------------------------------------------------

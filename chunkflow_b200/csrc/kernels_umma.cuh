@@ -64,7 +64,9 @@ struct ConvTail {
   float scale;              // 1, or 1/8 when the batch holds the 8 test-time-augmentation variants
 };
 void launch_conv3_umma(const __half* srcA, int ca, const __half* srcB, int cb, const PackedConv& w, __half* out,
-                       int nb, Int3 size, bool relu, cudaStream_t s, const ConvTail* tail = nullptr);
+                       int nb, Int3 size, bool relu, cudaStream_t s, const ConvTail* tail = nullptr, __half* pool_out = nullptr);
+// `pool_out` (optional; 16->16 and 32->32 layers): the (1,2,2) max-pooled output, CP8 of (Z, Y/2, X/2) -- written by the epilogue of
+// the TMEM-shift kernel itself (the pooled tensor never makes the extra HBM round trip), by maxpool_cp8 after the other variants.
 
 // ConvTranspose kernel = stride = (1,2,2) on tcgen05 (GEMM over input voxels + scatter epilogue).
 // h_w: (cin, cout, 1, 2, 2) fp32.  in: CP8 (nb, cin) of size in_size; out: CP8 (nb, cout) of (Z, 2Y, 2X).

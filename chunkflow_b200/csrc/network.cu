@@ -215,17 +215,20 @@ int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPo
     else launch_first_conv_cp8_from_patches(buf_in_, nb, s0, L.w, L.bias, h_e0a_, P, s);
     prof_end(s);
   }
-  auto conv = [&](const char* name, const __half* a, int ca, const __half* b, int cb, __half* out, Int3 sz) {
+  auto conv = [&](const char* name, const __half* a, int ca, const __half* b, int cb, __half* out, Int3 sz, __half* pool_out = nullptr) {
     const ConvLayer& L = layers_.at(name);
     prof_begin(name, s);
-    launch_conv3_umma(a, ca, b, cb, L.packed, out, nb, sz, /*relu=*/true, s);
+    launch_conv3_umma(a, ca, b, cb, L.packed, out, nb, sz, /*relu=*/true, s, nullptr, pool_out);
     prof_end(s);
   };
-  conv("enc0.2", h_e0a_, 16, nullptr, 0, h_e0_, s0);
-  prof_begin("pool0", s); launch_maxpool_cp8(h_e0_, h_p0_, 16, P, nb, s0, s); prof_end(s);
+  // the two encoder outputs feed a (1,2,2) max pool: fused into the convolution's epilogue unless CFB_NO_POOL_FUSION is set
+  const bool fuse_pool = getenv("CFB_NO_POOL_FUSION") == nullptr;
+  int launches_saved = 0;
+  conv("enc0.2", h_e0a_, 16, nullptr, 0, h_e0_, s0, fuse_pool ? h_p0_ : nullptr);
+  if (!fuse_pool) { prof_begin("pool0", s); launch_maxpool_cp8(h_e0_, h_p0_, 16, P, nb, s0, s); prof_end(s); } else ++launches_saved;
   conv("enc1.0", h_p0_, 16, nullptr, 0, h_e1a_, s1);
-  conv("enc1.2", h_e1a_, 32, nullptr, 0, h_e1_, s1);
-  prof_begin("pool1", s); launch_maxpool_cp8(h_e1_, h_p1_, 32, P, nb, s1, s); prof_end(s);
+  conv("enc1.2", h_e1a_, 32, nullptr, 0, h_e1_, s1, fuse_pool ? h_p1_ : nullptr);
+  if (!fuse_pool) { prof_begin("pool1", s); launch_maxpool_cp8(h_e1_, h_p1_, 32, P, nb, s1, s); prof_end(s); } else ++launches_saved;
   conv("enc2.0", h_p1_, 32, nullptr, 0, h_e2a_, s2);
   conv("enc2.2", h_e2a_, 64, nullptr, 0, h_e2_, s2);
   const bool simt_up = getenv("CFB_SIMT_CONVT") != nullptr;
@@ -243,12 +246,12 @@ int Network::forward_cp8(const void* chunk, int in_dtype, Int3 cs, const PatchPo
     prof_begin("dec0.2+head+blend", s);
     launch_conv3_umma(h_d0a_, 16, nullptr, 0, L.packed, h_d0_, nb, s0, /*relu=*/true, s, tail);
     prof_end(s);
-    return 14;
+    return 14 - launches_saved;
   }
   conv("dec0.2", h_d0a_, 16, nullptr, 0, h_d0_, s0);
-  if (!with_head) return 14;  // the head is fused into the blend kernel
+  if (!with_head) return 14 - launches_saved;  // the head is fused into the blend kernel
   { const ConvLayer& L = layers_.at("head"); prof_begin("head", s); launch_head_sigmoid_cp8(h_d0_, L.w, L.bias, net_out_, 16, cnet_, P, nb, s0, s); prof_end(s); }
-  return 15;
+  return 15 - launches_saved;
 }
 
 int Network::forward_from_chunk(const void* chunk, int in_dtype, Int3 cs, const PatchPos* patches, int nb, cudaStream_t s) {

@@ -1454,7 +1454,7 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
     }
   } else {
     // epilogue (warps 3..6 = set 0, 7..10 = set 1): the scatter of the four taps is a chain of tcgen05.ld, encode and
-    // 16-byte stores per tap -- the two warps of a lane quarter take two taps each
+    // 16-byte stores per tap -- the two warps of a lane quarter take one output row (y tap) each
     const int wq = warp & 3, eset = warp >= 7 ? 1 : 0;
     const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
     const int OY = 2 * p.Y, OX = 2 * p.X;
@@ -1473,7 +1473,7 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * BUF + g * ACC);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          if ((t & 1) != eset) continue;
+          if ((t >> 1) != eset) continue;  // a set takes one y tap = BOTH x taps: its threads fill whole 32-byte sectors (records 2x, 2x + 1)
           const size_t ovox = ((size_t)z * OY + (2 * (y0 + row) + (t >> 1))) * OX + (2 * (x0 + col) + (t & 1));
 #pragma unroll
           for (int cb = 0; cb < COUT / 16; ++cb) {

@@ -540,3 +540,17 @@ def test_f16f8_unfused_and_cuda_core_paths(monkeypatch, unet_model):
         err = np.abs(out - ref).max()
         print("f16f8", env, "max-abs vs oracle", err)
         assert err <= NET_ATOL_F32, env
+
+
+def test_network_on_float_and_uint16_chunks(unet_model):
+    """Input chunks that are not uint8 take the CUDA-core first layer (float32 input): float32 in [0, 1] as is, wider integers
+    normalised by their dtype maximum like the reference (inferencer.py:395-399)."""
+    rng = np.random.default_rng(43)
+    kw = dict(input_patch_size=(8, 32, 32), output_patch_overlap=(2, 8, 8), num_output_channels=3)
+    inf = _inferencer(model=MODEL_FILE, framework="b200", batch_size=3, **kw)
+    f = rng.random((12, 40, 48)).astype(np.float32)
+    o, _ = O.infer_chunk(f, framework="pytorch", model=unet_model, **kw)
+    assert np.abs(inf(Chunk(f)).array - o).max() <= NET_ATOL_F32
+    u16 = (rng.random((12, 40, 48)) * 65535).astype(np.uint16)
+    o16, _ = O.infer_chunk(u16, framework="pytorch", model=unet_model, **kw)
+    assert np.abs(inf(Chunk(u16)).array - o16).max() <= NET_ATOL_F32

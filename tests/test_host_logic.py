@@ -206,3 +206,26 @@ def test_mask_conversion_preserves_numpy_semantics():
     # numpy itself refuses the first two of those
     with pytest.raises(TypeError):
         a = np.ones(3, np.uint8); a *= np.ones(3, np.int32)
+
+
+def test_result_array_is_recycled_only_when_the_caller_dropped_it():
+    """Inferencer._result_array: the previous result array is handed out again only when nothing references it any more
+    (a view of it counts); see the method's docstring for why (12.9 GB results, page faults and munmap inside a VM)."""
+    from chunkflow_b200.flow.divid_conquer.inferencer import Inferencer
+
+    class Holder:
+        pass
+    h = Holder()
+    shape = (3, 64, 512, 512)     # 201 MB: above the 64 MB threshold
+    a = Inferencer._result_array(h, shape)
+    addr = a.ctypes.data
+    view = a[:-1]
+    del a
+    b = Inferencer._result_array(h, shape)
+    assert b.ctypes.data != addr, "a result that is still referenced (through a view) must not be recycled"
+    addr_b = b.ctypes.data
+    del view, b
+    c = Inferencer._result_array(h, shape)
+    assert c.ctypes.data == addr_b, "a dropped result array is handed out again"
+    d = Inferencer._result_array(h, (3, 8, 8, 8))
+    assert d.shape == (3, 8, 8, 8) and getattr(h, "_last_result", None) is None or h._last_result is not d   # small results are not kept

@@ -136,32 +136,33 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// 16 channels of one voxel -> the records of the output format (chunk pair 0, 1 of patch b)
-__device__ __forceinline__ void store_voxel16(int fmt, const float (&v)[16], int b, size_t vox, size_t plane_vox, uint4* __restrict__ out16) {
-  if (fmt == kFmtF16F8) {
+// 16 channels of one voxel -> the records of the output format FMT; pl[k] = base of plane k of this patch's two 8-channel
+// chunks (hoisted out of the voxel loop: the 64-bit plane products were a third of the epilogue's instructions)
+template <int FMT>
+__device__ __forceinline__ void store_voxel16(const float (&v)[16], uint4* const (&pl)[4], size_t vox) {
+  if constexpr (FMT == kFmtF16F8) {
     uint4 h0, h1, a8, l8;
     af_encode16(v, h0, h1, a8, l8);
-    const size_t plane = (size_t)b * 4;
-    out16[plane * plane_vox + vox] = h0;
-    out16[(plane + 1) * plane_vox + vox] = a8;
-    out16[(plane + 2) * plane_vox + vox] = h1;
-    out16[(plane + 3) * plane_vox + vox] = l8;
-    return;
-  }
-  const int P = fmt == kFmtF16x2 ? 2 : 1;
+    pl[0][vox] = h0;
+    pl[1][vox] = a8;
+    pl[2][vox] = h1;
+    pl[3][vox] = l8;
+  } else {
+    constexpr int P = FMT == kFmtF16x2 ? 2 : 1;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    float hi[8];
+    for (int h = 0; h < 2; ++h) {
+      float hi[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
-    const size_t plane = ((size_t)b * 2 + h) * P;
-    out16[plane * plane_vox + vox] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
-    if (P == 2)
-      out16[(plane + 1) * plane_vox + vox] = make_uint4(pack_h2(v[h * 8] - hi[0], v[h * 8 + 1] - hi[1]), pack_h2(v[h * 8 + 2] - hi[2], v[h * 8 + 3] - hi[3]),
-                                                        pack_h2(v[h * 8 + 4] - hi[4], v[h * 8 + 5] - hi[5]), pack_h2(v[h * 8 + 6] - hi[6], v[h * 8 + 7] - hi[7]));
+      for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
+      pl[h * P][vox] = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]), pack_h2(hi[6], hi[7]));
+      if constexpr (P == 2)
+        pl[h * P + 1][vox] = make_uint4(pack_h2(v[h * 8] - hi[0], v[h * 8 + 1] - hi[1]), pack_h2(v[h * 8 + 2] - hi[2], v[h * 8 + 3] - hi[3]),
+                                        pack_h2(v[h * 8 + 4] - hi[4], v[h * 8 + 5] - hi[5]), pack_h2(v[h * 8 + 6] - hi[6], v[h * 8 + 7] - hi[7]));
+    }
   }
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1) first_conv_ts_kernel(const FirstTsParams p) {
   __shared__ __align__(128) uint8_t s_planes[kRing * kSlotBytes];
   __shared__ __align__(128) uint8_t s_w[kWBytes];
@@ -321,6 +322,10 @@ __global__ void __launch_bounds__(kThreads, 1) first_conv_ts_kernel(const FirstT
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       const int b = item / ncols, col = item % ncols;
       const int x0 = (col % p.tiles_x) * kXT, y0 = (col / p.tiles_x) * kTY;
+      constexpr int NPL = FMT == kFmtF16 ? 2 : 4;   // planes of the patch's 16 channels
+      uint4* planes[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) planes[k] = out16 + ((size_t)b * NPL + (k < NPL ? k : 0)) * plane_vox;
       for (int pl = 0; pl < Z; ++pl, ++gi) {
         const uint32_t ab = gi % kAccs;
         mbar_wait(BAR(kAccF + ab), (gi / kAccs) & 1u);
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) first_conv_ts_kernel(const FirstT
               const float t = fmaf(__uint_as_float(r[i]), 1.0f / 255.0f, bias[i]);  // the reference divides the INPUT by 255 (inferencer.py:395-399)
               v[i] = t < 0.f ? 0.f : t;                                             // ReLU; NaN passes, like torch.relu
             }
-            store_voxel16(p.fmt, v, b, ((size_t)pl * Y + y) * X + x, plane_vox, out16);
+            store_voxel16<FMT>(v, planes, ((size_t)pl * Y + y) * X + x);
           }
         }
         tc_fence_before();
@@ -390,7 +395,10 @@ void launch_first_conv_ts(const void* chunk_u8, Int3 cs, const PatchPos* patches
   int dev = 0, sms = 148;
   CFB_CUDA(cudaGetDevice(&dev));
   CFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  first_conv_ts_kernel<<<std::min(p.total_items, sms), kThreads, 0, s>>>(p);
+  const int grid = std::min(p.total_items, sms);
+  if (fmt == kFmtF16F8) first_conv_ts_kernel<kFmtF16F8><<<grid, kThreads, 0, s>>>(p);
+  else if (fmt == kFmtF16x2) first_conv_ts_kernel<kFmtF16x2><<<grid, kThreads, 0, s>>>(p);
+  else first_conv_ts_kernel<kFmtF16><<<grid, kThreads, 0, s>>>(p);
   CFB_LAUNCH_CHECK();
 }
 

@@ -1471,6 +1471,35 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
         const int row = __float2int_rd(((float)qpos + 0.5f) * inv_xt), col = qpos - row * p.XT;
         const bool valid = row < ty_valid && col < xt_valid;
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * BUF + g * ACC);
+        if constexpr (F8) {
+          // f16f8: the two x taps of this set's output row are adjacent 16-byte records of every plane -> encode both and write
+          // each plane with ONE 32-byte store (st.global.v8.b32): whole sectors, half the store instructions
+          const size_t ovox = ((size_t)z * OY + (2 * (y0 + row) + eset)) * OX + 2 * (x0 + col);
+#pragma unroll
+          for (int cb = 0; cb < COUT / 16; ++cb) {
+            uint4 rec[2][4];
+#pragma unroll
+            for (int bx = 0; bx < 2; ++bx) {
+              uint32_t r[16];
+              tc_ld16(taddr + (eset * 2 + bx) * COUT + cb * 16, r);
+              tc_wait_ld();
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(r[i]), p.acc_scale, __ldg(p.bias + cb * 16 + i));
+              af_encode16(v, rec[bx][0], rec[bx][2], rec[bx][1], rec[bx][3]);  // plane order: H 0..7, A8, H 8..15, L8
+            }
+            if (valid) {
+              const size_t plane = ((size_t)b * (COUT / 8) + cb * 2) * 2;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4* dst = out16 + (plane + k) * oplane_vox + ovox;
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(rec[0][k].x), "r"(rec[0][k].y),
+                             "r"(rec[0][k].z), "r"(rec[0][k].w), "r"(rec[1][k].x), "r"(rec[1][k].y), "r"(rec[1][k].z), "r"(rec[1][k].w)
+                             : "memory");
+              }
+            }
+          }
+        } else
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           if ((t >> 1) != eset) continue;  // a set takes one y tap = BOTH x taps: its threads fill whole 32-byte sectors (records 2x, 2x + 1)

@@ -643,16 +643,21 @@ int cfb_infer_chunk_host(cfb_handle h, const void* h_in, int32_t in_dtype, int64
     ensure(h->d_host_in, h->host_in_cap, in_bytes);
     ensure(h->d_host_out, h->host_out_cap, out_bytes);
     cudaStream_t s = h->own_stream;
+    // host arrays in pageable memory (what a drop-in caller has: plain numpy) move through the engine's own pinned ring,
+    // copied by host threads; CFB_NO_HOST_STAGING=1 leaves the staging to the driver
+    static const bool no_staging = getenv("CFB_NO_HOST_STAGING") != nullptr;
     CFB_CUDA(cudaEventRecord(h->ev[4], s));
-    CFB_CUDA(cudaMemcpyAsync(h->d_host_in, h_in, in_bytes, cudaMemcpyHostToDevice, s));
+    if (!no_staging && in_bytes >= ((size_t)64 << 20) && !is_pinned_host(h_in)) {
+      if (!h->stager) h->stager = std::make_unique<HostStager>(h->p.device);
+      h->stager->upload(h_in, h->d_host_in, in_bytes, s);
+    } else {
+      CFB_CUDA(cudaMemcpyAsync(h->d_host_in, h_in, in_bytes, cudaMemcpyHostToDevice, s));
+    }
     CFB_CUDA(cudaEventRecord(h->ev[5], s));
     Progressive pg;
     pg.h_out = h_out;
     pg.copy_stream = h->copy_stream;
     pg.ready = h->ev_ready;
-    // a result array in pageable memory (what a drop-in caller has: a fresh np.empty) is filled through the
-    // engine's own pinned ring by host threads; CFB_NO_HOST_STAGING=1 leaves the staging to the driver
-    static const bool no_staging = getenv("CFB_NO_HOST_STAGING") != nullptr;
     if (!no_staging && out_bytes >= ((size_t)8 << 20) && !is_pinned_host(h_out)) {
       if (!h->stager) h->stager = std::make_unique<HostStager>(h->p.device);
       pg.stager = h->stager.get();

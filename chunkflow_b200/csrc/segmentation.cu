@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <type_traits>
+#include <vector>
 
 #include "chunkflow_b200.h"
 #include "common.cuh"
@@ -38,30 +39,7 @@ __device__ __forceinline__ uint32_t fg_value(const T* __restrict__ in, int64_t i
   }
 }
 
-__device__ __forceinline__ uint32_t uf_find(const uint32_t* P, uint32_t x) {
-  uint32_t p = P[x];
-  while (p != x) { x = p; p = P[x]; }
-  return x;
-}
-
-__device__ __forceinline__ void uf_unite(uint32_t* P, uint32_t a, uint32_t b) {
-  bool done = false;
-  do {
-    a = uf_find(P, a);
-    b = uf_find(P, b);
-    if (a < b) {
-      const uint32_t old = atomicMin(&P[b], a);
-      done = old == b;
-      b = old;
-    } else if (b < a) {
-      const uint32_t old = atomicMin(&P[a], b);
-      done = old == a;
-      a = old;
-    } else {
-      done = true;
-    }
-  } while (!done);
-}
+#include "watershed_kernels.cuh"  // union-find helpers + the watershed / region-graph / relabel kernels
 
 template <typename T>
 __global__ void __launch_bounds__(kT) cc_init_kernel(const T* __restrict__ in, uint32_t* __restrict__ P, uint32_t* __restrict__ val,
@@ -175,6 +153,32 @@ __global__ void __launch_bounds__(kT) cc_relabel_kernel(const uint32_t* __restri
     out[i] = val[i] ? rank[P[i]] + 1u : 0u;
 }
 
+WsGeom ws_geom(int64_t z, int64_t y, int64_t x) {
+  if (z <= 0 || y <= 0 || x <= 0 || z > INT32_MAX || y > INT32_MAX || x > INT32_MAX) throw std::invalid_argument("bad volume size");
+  WsGeom g;
+  g.sz = Int3{(int)z, (int)y, (int)x};
+  g.n = z * y * x;
+  if (g.n >= (int64_t)UINT32_MAX) throw std::invalid_argument("more than 2^32 - 1 voxels");
+  g.step[0] = y * x; g.step[1] = x; g.step[2] = 1;
+  return g;
+}
+
+template <typename F>
+int guarded_seg(F&& f) {
+  try {
+    return f();
+  } catch (const std::invalid_argument& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_INVALID_ARGUMENT;
+  } catch (const CudaError& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_CUDA;
+  } catch (const std::exception& ex) {
+    set_last_error(ex.what());
+    return CFB_ERR_UNSUPPORTED;
+  }
+}
+
 int grid_for(int64_t items) {
   int64_t b = ceil_div64(items, kT);
   return (int)std::max<int64_t>(1, std::min<int64_t>(b, 148 * 16));
@@ -241,4 +245,154 @@ extern "C" int64_t cfb_connected_components_workspace(int64_t z, int64_t y, int6
   if (z <= 0 || y <= 0 || x <= 0) return 0;
   const int64_t n = z * y * x;
   return (3 * n + ceil_div64(n, kScanBlock) + 1) * (int64_t)sizeof(uint32_t);
+}
+
+// ---- watershed fragments ------------------------------------------------------------------
+extern "C" int64_t cfb_watershed_workspace(int64_t z, int64_t y, int64_t x) {
+  if (z <= 0 || y <= 0 || x <= 0) return 0;
+  const int64_t n = z * y * x;   // the connected-components workspace + the plateau distances + one flag
+  return cfb_connected_components_workspace(z, y, x) + (n + 1) * (int64_t)sizeof(uint32_t);
+}
+
+extern "C" int cfb_watershed_device(const float* d_affs, int32_t flip_channel, int64_t z, int64_t y, int64_t x, float aff_threshold_low,
+                                    float aff_threshold_high, uint32_t* d_fragments, void* d_workspace, uint32_t* num_fragments,
+                                    void* stream) {
+  return guarded_seg([&]() -> int {
+    if (!d_affs || !d_fragments || !d_workspace) throw std::invalid_argument("watershed: null argument");
+    if (!(aff_threshold_low < aff_threshold_high)) throw std::invalid_argument("watershed: need aff_threshold_low < aff_threshold_high");
+    const WsGeom g = ws_geom(z, y, x);
+    const int64_t n = g.n;
+    cudaStream_t s = (cudaStream_t)stream;
+    uint32_t* P = static_cast<uint32_t*>(d_workspace);
+    uint32_t* val = P + n;
+    uint32_t* rank = val + n;
+    const int64_t nblocks = ceil_div64(n, kScanBlock);
+    uint32_t* block_count = rank + n;
+    uint32_t* d_num = block_count + nblocks;
+    uint32_t* dist = d_num + 1;
+    uint32_t* d_changed = dist + n;
+    const int grid = grid_for(n);
+    ws_bits_kernel<<<grid, kT, 0, s>>>(d_affs, g, flip_channel ? 1 : 0, aff_threshold_low, aff_threshold_high, P, val);
+    CFB_LAUNCH_CHECK();
+    ws_corner_kernel<<<grid, kT, 0, s>>>(val, g, dist);
+    CFB_LAUNCH_CHECK();
+    // breadth-first levels in batches of 8 launches per look at the flag (a level without news ends the search; the
+    // remaining launches of its batch find nothing)
+    uint32_t level = 1;
+    for (;;) {
+      CFB_CUDA(cudaMemsetAsync(d_changed, 0, sizeof(uint32_t), s));
+      for (int k = 0; k < 8; ++k, ++level) {
+        ws_bfs_kernel<<<grid, kT, 0, s>>>(val, g, dist, level, d_changed);
+        CFB_LAUNCH_CHECK();
+      }
+      uint32_t changed = 0;
+      CFB_CUDA(cudaMemcpyAsync(&changed, d_changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CFB_CUDA(cudaStreamSynchronize(s));
+      if (!changed) break;
+      if (level > 0x7FFFFFF0u) throw std::runtime_error("watershed: plateau search did not end");
+    }
+    ws_merge_kernel<<<grid, kT, 0, s>>>(val, dist, g, P);
+    CFB_LAUNCH_CHECK();
+    cc_flatten_count_kernel<<<(unsigned)nblocks, kT, 0, s>>>(val, P, n, block_count);
+    CFB_LAUNCH_CHECK();
+    cc_scan_blocks_kernel<<<1, 1024, 0, s>>>(block_count, nblocks, d_num);
+    CFB_LAUNCH_CHECK();
+    cc_rank_kernel<<<(unsigned)nblocks, kT, 0, s>>>(val, P, n, block_count, rank);
+    CFB_LAUNCH_CHECK();
+    cc_relabel_kernel<<<grid, kT, 0, s>>>(val, P, rank, d_fragments, n);
+    CFB_LAUNCH_CHECK();
+    if (num_fragments) {
+      CFB_CUDA(cudaMemcpyAsync(num_fragments, d_num, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      CFB_CUDA(cudaStreamSynchronize(s));
+    }
+    return CFB_OK;
+  });
+}
+
+// ---- region graph -------------------------------------------------------------------------
+// workspace: table keys | table sums | compact keys | compact sums (8 B each) | table counts | compact counts | info[4] (4 B each)
+extern "C" int64_t cfb_region_graph_workspace(int64_t table_slots) {
+  if (table_slots <= 0) return 0;
+  return table_slots * (4 * 8 + 2 * 4) + 4 * (int64_t)sizeof(uint32_t);
+}
+
+extern "C" int cfb_region_graph_device(const float* d_affs, int32_t flip_channel, const uint32_t* d_fragments, int64_t z, int64_t y,
+                                       int64_t x, void* d_workspace, int64_t table_slots, int64_t* num_edges, void* stream) {
+  return guarded_seg([&]() -> int {
+    if (!d_affs || !d_fragments || !d_workspace || !num_edges) throw std::invalid_argument("region graph: null argument");
+    if (table_slots < 2 || (table_slots & (table_slots - 1)) || table_slots >= ((int64_t)1 << 31))
+      throw std::invalid_argument("region graph: table_slots must be a power of two below 2^31");
+    const WsGeom g = ws_geom(z, y, x);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* keys = static_cast<unsigned long long*>(d_workspace);
+    unsigned long long* sums = keys + table_slots;
+    uint32_t* counts = reinterpret_cast<uint32_t*>(keys + 4 * table_slots);
+    uint32_t* info = counts + 2 * table_slots;
+    CFB_CUDA(cudaMemsetAsync(keys, 0, (size_t)table_slots * 16, s));     // keys + sums
+    CFB_CUDA(cudaMemsetAsync(counts, 0, (size_t)table_slots * 4, s));
+    CFB_CUDA(cudaMemsetAsync(info, 0, 4 * sizeof(uint32_t), s));
+    rg_accumulate_kernel<<<grid_for(g.n), kT, 0, s>>>(d_affs, d_fragments, g, flip_channel ? 1 : 0, keys, sums, counts,
+                                                     (unsigned long long)(table_slots - 1), info);
+    CFB_LAUNCH_CHECK();
+    uint32_t h_info[2] = {0, 0};
+    CFB_CUDA(cudaMemcpyAsync(h_info, info, sizeof(h_info), cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaStreamSynchronize(s));
+    *num_edges = h_info[0];
+    if (h_info[1]) {
+      set_last_error("region graph: the hash table is too small for this many fragment pairs");
+      return CFB_ERR_CAPACITY;
+    }
+    return CFB_OK;
+  });
+}
+
+extern "C" int cfb_region_graph_read(void* d_workspace, int64_t table_slots, int64_t num_edges, uint32_t* h_u, uint32_t* h_v,
+                                     uint64_t* h_sum_fixed, uint32_t* h_count, void* stream) {
+  return guarded_seg([&]() -> int {
+    if (!d_workspace || table_slots < 2 || num_edges < 0 || num_edges > table_slots) throw std::invalid_argument("region graph read: bad argument");
+    if (num_edges == 0) return CFB_OK;
+    if (!h_u || !h_v || !h_sum_fixed || !h_count) throw std::invalid_argument("region graph read: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long* keys = static_cast<unsigned long long*>(d_workspace);
+    unsigned long long* sums = keys + table_slots;
+    unsigned long long* okeys = sums + table_slots;
+    unsigned long long* osums = okeys + table_slots;
+    uint32_t* counts = reinterpret_cast<uint32_t*>(keys + 4 * table_slots);
+    uint32_t* ocounts = counts + table_slots;
+    uint32_t* cursor = ocounts + table_slots + 2;   // info[2]
+    CFB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), s));
+    rg_gather_kernel<<<grid_for(table_slots), kT, 0, s>>>(keys, sums, counts, table_slots, okeys, osums, ocounts, cursor);
+    CFB_LAUNCH_CHECK();
+    std::vector<unsigned long long> k((size_t)num_edges), sm((size_t)num_edges);
+    std::vector<uint32_t> ct((size_t)num_edges);
+    uint32_t got = 0;
+    CFB_CUDA(cudaMemcpyAsync(&got, cursor, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaMemcpyAsync(k.data(), okeys, (size_t)num_edges * 8, cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaMemcpyAsync(sm.data(), osums, (size_t)num_edges * 8, cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaMemcpyAsync(ct.data(), ocounts, (size_t)num_edges * 4, cudaMemcpyDeviceToHost, s));
+    CFB_CUDA(cudaStreamSynchronize(s));
+    if ((int64_t)got != num_edges) throw std::invalid_argument("region graph read: num_edges does not match the table");
+    std::vector<uint32_t> order((size_t)num_edges);
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return k[a] < k[b]; });   // the gather order is arbitrary
+    for (size_t i = 0; i < order.size(); ++i) {
+      const uint32_t o = order[i];
+      h_u[i] = (uint32_t)(k[o] >> 32);
+      h_v[i] = (uint32_t)(k[o] & 0xFFFFFFFFULL);
+      h_sum_fixed[i] = sm[o];
+      h_count[i] = ct[o];
+    }
+    return CFB_OK;
+  });
+}
+
+extern "C" int cfb_relabel_device(const uint32_t* d_labels, int64_t n, const uint32_t* d_map, int64_t map_size, uint32_t* d_out,
+                                  void* stream) {
+  return guarded_seg([&]() -> int {
+    if (!d_labels || !d_map || !d_out || n < 0 || map_size < 0 || map_size > (int64_t)UINT32_MAX) throw std::invalid_argument("relabel: bad argument");
+    if (n == 0) return CFB_OK;
+    relabel_map_kernel<<<grid_for(n), kT, 0, (cudaStream_t)stream>>>(d_labels, n, d_map, (uint32_t)map_size, d_out);
+    CFB_LAUNCH_CHECK();
+    return CFB_OK;
+  });
 }

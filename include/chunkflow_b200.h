@@ -20,6 +20,8 @@
  *   cfb_patch_forward_host        PatchInferencer.__call__ plugin level
  *                                 patch/pytorch.py:98-119, patch/universal.py:60-69, patch/identity.py:30-51
  *   cfb_device_name               Inferencer.compute_device   inferencer.py:173-175
+ *   cfb_watershed_device, cfb_region_graph_*, cfb_agglomerate_edges_host, cfb_relabel_device
+ *                                 plugins/agglomerate.py:8-48 (execute -> waterz.agglomerate)
  *
  * Plain pointers and sizes only -- no torch types.  Device pointers are raw CUDA device
  * addresses (e.g. torch.Tensor.data_ptr()) owned by the caller.  All functions return
@@ -42,6 +44,7 @@ extern "C" {
 #define CFB_ERR_WEIGHTS (-3)
 #define CFB_ERR_OUTPUT_RANGE (-4) /* some output >= 1.0001 (reference inferencer.py:465-466) */
 #define CFB_ERR_UNSUPPORTED (-5)
+#define CFB_ERR_CAPACITY (-6) /* a caller-sized table is too small: call again with a larger one */
 
 /* framework: which patch backend runs on the device */
 #define CFB_FRAMEWORK_UNET3L 0   /* fixed 3-level 3D U-Net (chunkflow_b200/convnet/unet3l.py) */
@@ -248,6 +251,49 @@ int cfb_connected_components_device(const void* d_in, int32_t in_dtype, int64_t 
                                     int32_t connectivity, uint32_t* d_labels, void* d_workspace, uint32_t* num_labels,
                                     void* stream);
 int64_t cfb_connected_components_workspace(int64_t z, int64_t y, int64_t x);
+
+/* `agglomerate`: the reference's plugin (chunkflow/plugins/agglomerate.py:8-48) hands the affinity
+ * map to waterz.agglomerate(affs, [threshold], fragments=, aff_threshold_low=, aff_threshold_high=,
+ * scoring_function='OneMinus<MeanAffinity<RegionGraphType, ScoreValue>>') -- watershed fragments, region graph,
+ * hierarchical merging.  waterz is a third-party package that is not vendored in the reference tree; its published algorithm
+ * is restated in oracle/agglomeration_oracle.py ("parity unpinned").  Four steps, the voxel passes on the device:
+ *
+ * d_affs: (3, z, y, x) float32.  flip_channel != 0: the channels are in chunkflow's order x, y, z (the plugin's
+ * `flip_channel`, agglomerate.py:26-29: waterz wants z, y, x) and are read in reverse instead of being copied.
+ *
+ * cfb_watershed_device: steepest-ascent watershed (waterz backend/watershed.hpp; Zlateski & Seung, arXiv:1505.00249) ->
+ * d_fragments (z,y,x) uint32, basins numbered 1..N in raster order of their first voxel, 0 = voxels whose strongest edge does
+ * not exceed aff_threshold_low.  Plateau interiors drain towards the neighbour one breadth-first step closer to a plateau
+ * corner (order independent; the sequential code's queue order is not reproduced, see the oracle).  d_workspace:
+ * cfb_watershed_workspace(z,y,x) bytes.  num_fragments (host, may be NULL; the stream is synchronised either way). */
+int64_t cfb_watershed_workspace(int64_t z, int64_t y, int64_t x);
+int cfb_watershed_device(const float* d_affs, int32_t flip_channel, int64_t z, int64_t y, int64_t x, float aff_threshold_low,
+                         float aff_threshold_high, uint32_t* d_fragments, void* d_workspace, uint32_t* num_fragments,
+                         void* stream);
+
+/* Region graph (waterz backend/region_graph.hpp with the MeanAffinity statistics): for every pair of touching fragments
+ * (6-neighbourhood, ids != 0) the SUM of the affinities on the faces between them, in 2^-30 fixed point (each affinity clamped
+ * to [0,1], NaN = 0, rounded to nearest even: the sum does not depend on the order of the atomics), and their COUNT.  Built in
+ * an open-addressing table of `table_slots` (a power of two) slots inside d_workspace (cfb_region_graph_workspace(table_slots)
+ * bytes); returns CFB_ERR_CAPACITY when the table is too full -- call again with more slots.  *num_edges = pairs found.
+ * cfb_region_graph_read copies the edges to the host, sorted by (u, v), u < v. */
+int64_t cfb_region_graph_workspace(int64_t table_slots);
+int cfb_region_graph_device(const float* d_affs, int32_t flip_channel, const uint32_t* d_fragments, int64_t z, int64_t y, int64_t x,
+                            void* d_workspace, int64_t table_slots, int64_t* num_edges, void* stream);
+int cfb_region_graph_read(void* d_workspace, int64_t table_slots, int64_t num_edges, uint32_t* h_u, uint32_t* h_v,
+                          uint64_t* h_sum_fixed, uint32_t* h_count, void* stream);
+
+/* The merge loop (waterz backend/IterativeRegionMerging.hpp, scoring function OneMinus<MeanAffinity>), on the HOST like
+ * waterz's own: repeatedly merge the edge with the smallest score 1 - sum / (count * 2^30) (ties: smaller ids first) until
+ * the smallest score reaches `threshold`; the larger id is merged into the smaller one, edges to a common neighbour pool
+ * their statistics.  root_of[i], i < num_nodes (= largest fragment id + 1), receives the id node i ends up with
+ * (root_of[0] == 0).  No GPU involved. */
+int cfb_agglomerate_edges_host(int64_t num_nodes, int64_t num_edges, const uint32_t* u, const uint32_t* v,
+                               const uint64_t* sum_fixed, const uint32_t* count, float threshold, uint32_t* root_of);
+
+/* d_out[i] = d_map[d_labels[i]] (labels >= map_size pass through): applies root_of to the fragments. */
+int cfb_relabel_device(const uint32_t* d_labels, int64_t n, const uint32_t* d_map, int64_t map_size, uint32_t* d_out,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,8 @@ int guarded_op(F&& f) {
 // Per-section 256-bin histogram.  grid = (blocks per section, Z).  32 lane-private sub-histograms interleaved so that
 // counter (bin, lane) sits in bank `lane`: the shared-memory atomics of one warp instruction never conflict (a single
 // shared table serialises ~3.5x on the birthday collisions of 32 lanes in 32 banks).  Algorithmic traffic: 1 B / voxel.
+constexpr int kMlp = 4;  // independent 16-byte accesses per thread and loop trip of the streaming kernels below
+
 __global__ void __launch_bounds__(256) section_hist_kernel(const uint8_t* __restrict__ img, int64_t section_elems,
                                                            unsigned long long* __restrict__ hist) {
   __shared__ unsigned int sh[256 * 32];
@@ -64,8 +66,7 @@ __global__ void __launch_bounds__(256) section_hist_kernel(const uint8_t* __rest
   const int64_t head = section_elems < head_want ? section_elems : head_want;
   const int64_t nvec = (section_elems - head) / 16;
   const uint4* v = reinterpret_cast<const uint4*>(sec + head);
-  for (int64_t i = tid; i < nvec; i += stride) {
-    const uint4 q = __ldg(v + i);
+  auto count16 = [&](const uint4 q) {
     const unsigned int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -74,7 +75,18 @@ __global__ void __launch_bounds__(256) section_hist_kernel(const uint8_t* __rest
       atomicAdd(mine + (((w[k] >> 16) & 255u) << 5), 1u);
       atomicAdd(mine + ((w[k] >> 24) << 5), 1u);
     }
+  };
+  // the shared-memory atomics order the loop body, so the loads of later vectors cannot be hoisted by the compiler:
+  // kMlp independent 16-byte loads are issued first (bytes in flight per SM, not the atomics, were the limit)
+  int64_t i = tid;
+  for (; i + (kMlp - 1) * stride < nvec; i += kMlp * stride) {
+    uint4 q[kMlp];
+#pragma unroll
+    for (int k = 0; k < kMlp; ++k) q[k] = __ldg(v + i + k * stride);
+#pragma unroll
+    for (int k = 0; k < kMlp; ++k) count16(q[k]);
   }
+  for (; i < nvec; i += stride) count16(__ldg(v + i));
   for (int64_t i = tid; i < head; i += stride) atomicAdd(mine + ((unsigned int)sec[i] << 5), 1u);
   for (int64_t i = head + nvec * 16 + tid; i < section_elems; i += stride) atomicAdd(mine + ((unsigned int)sec[i] << 5), 1u);
   __syncthreads();
@@ -192,15 +204,23 @@ __global__ void __launch_bounds__(256) apply_lut_kernel(uint8_t* __restrict__ im
   const int64_t head = section_elems < head_want ? section_elems : head_want;
   const int64_t nvec = (section_elems - head) / 16;
   uint4* v = reinterpret_cast<uint4*>(sec + head);
-  for (int64_t i = tid; i < nvec; i += stride) {
-    uint4 q = v[i];
+  auto map16 = [&](const uint4 q) {
     unsigned int w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       w[k] = lut[(w[k] & 255u) << 5] | (lut[((w[k] >> 8) & 255u) << 5] << 8) | (lut[((w[k] >> 16) & 255u) << 5] << 16) |
              (lut[(w[k] >> 24) << 5] << 24);
-    v[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  int64_t i = tid;
+  for (; i + (kMlp - 1) * stride < nvec; i += kMlp * stride) {   // kMlp loads in flight before the first store (in place: img is read and written)
+    uint4 q[kMlp];
+#pragma unroll
+    for (int k = 0; k < kMlp; ++k) q[k] = v[i + k * stride];
+#pragma unroll
+    for (int k = 0; k < kMlp; ++k) v[i + k * stride] = map16(q[k]);
   }
+  for (; i < nvec; i += stride) v[i] = map16(v[i]);
   for (int64_t i = tid; i < head; i += stride) sec[i] = (uint8_t)lut[(unsigned int)sec[i] << 5];
   for (int64_t i = head + nvec * 16 + tid; i < section_elems; i += stride) sec[i] = (uint8_t)lut[(unsigned int)sec[i] << 5];
 }
@@ -224,31 +244,52 @@ __global__ void __launch_bounds__(256) maskout_kernel(T* __restrict__ chunk, int
   constexpr int V = 16 / sizeof(T);
   const int64_t planes = rows / Y;  // channels * Z
   const int rpb = 256 / tpr, rsub = threadIdx.x / tpr, tx = threadIdx.x % tpr;
-  for (int64_t cz = blockIdx.y; cz < planes; cz += gridDim.y)
-  for (int y = blockIdx.x * rpb + rsub; y < Y; y += gridDim.x * rpb) {
+  const int ystep = gridDim.x * rpb;
+  // rows whose pitch keeps every row start 16-byte aligned take the vector path with kMlp rows per thread and trip: all
+  // their 16-byte loads are issued before the first multiply / store (in-place streams are bound by the bytes in flight)
+  const bool rows_aligned = (reinterpret_cast<uintptr_t>(chunk) & 15) == 0 && ((int64_t)X * sizeof(T)) % 16 == 0;
+  for (int64_t cz = blockIdx.y; cz < planes; cz += gridDim.y) {
     const int z = (int)(cz % Z);
-    T* prow = chunk + (cz * Y + y) * X;
-    const M* mrow = mask + ((int64_t)(z / fz) * MY + (y / fy)) * MX;
-    const bool aligned = (reinterpret_cast<uintptr_t>(prow) & 15) == 0;
-    for (int x0 = tx * V; x0 < X; x0 += tpr * V) {
-      T* p = prow + x0;
-      int q = x0 / fx, r = x0 - q * fx;
-      if (aligned && x0 + V <= X) {
-        uint4 pack = *reinterpret_cast<uint4*>(p);
-        T e[V];
-        memcpy(e, &pack, 16);
-        M m = __ldg(mrow + q);  // one mask load per run of fx voxels
+    const M* mplane = mask + (int64_t)(z / fz) * MY * MX;
+    for (int y0 = blockIdx.x * rpb + rsub; y0 < Y; y0 += kMlp * ystep) {
+      if (rows_aligned) {
+        for (int x0 = tx * V; x0 < X; x0 += tpr * V) {   // X % V == 0 here: every vector is whole
+          uint4 pack[kMlp];
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-          e[k] = mul_as<T, M>(e[k], m);
-          if (++r == fx) { r = 0; ++q; if (k + 1 < V) m = __ldg(mrow + q); }
+          for (int u = 0; u < kMlp; ++u)
+            if (y0 + u * ystep < Y) pack[u] = *reinterpret_cast<const uint4*>(chunk + (cz * Y + y0 + u * ystep) * X + x0);
+#pragma unroll
+          for (int u = 0; u < kMlp; ++u) {
+            const int y = y0 + u * ystep;
+            if (y >= Y) continue;
+            const M* mrow = mplane + (int64_t)(y / fy) * MX;
+            int q = x0 / fx, r = x0 - q * fx;
+            T e[V];
+            memcpy(e, &pack[u], 16);
+            M m = __ldg(mrow + q);  // one mask load per run of fx voxels
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              e[k] = mul_as<T, M>(e[k], m);
+              if (++r == fx) { r = 0; ++q; if (k + 1 < V) m = __ldg(mrow + q); }
+            }
+            memcpy(&pack[u], e, 16);
+            *reinterpret_cast<uint4*>(chunk + (cz * Y + y) * X + x0) = pack[u];
+          }
         }
-        memcpy(&pack, e, 16);
-        *reinterpret_cast<uint4*>(p) = pack;
       } else {
-        for (int k = 0; k < V && x0 + k < X; ++k) {
-          p[k] = mul_as<T, M>(p[k], __ldg(mrow + q));
-          if (++r == fx) { r = 0; ++q; }
+        for (int u = 0; u < kMlp; ++u) {
+          const int y = y0 + u * ystep;
+          if (y >= Y) break;
+          T* prow = chunk + (cz * Y + y) * X;
+          const M* mrow = mplane + (int64_t)(y / fy) * MX;
+          for (int x0 = tx * V; x0 < X; x0 += tpr * V) {
+            T* p = prow + x0;
+            int q = x0 / fx, r = x0 - q * fx;
+            for (int k = 0; k < V && x0 + k < X; ++k) {
+              p[k] = mul_as<T, M>(p[k], __ldg(mrow + q));
+              if (++r == fx) { r = 0; ++q; }
+            }
+          }
         }
       }
     }

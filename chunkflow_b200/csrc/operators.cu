@@ -9,6 +9,7 @@
 // including its quirks (normalize_contrast: the whole-array pass also runs after the per-section pass; 255-bin histograms).
 #include <algorithm>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "chunkflow_b200.h"
@@ -264,6 +265,24 @@ __global__ void __launch_bounds__(256) maskout_kernel(T* __restrict__ chunk, int
             if (y >= Y) continue;
             const M* mrow = mplane + (int64_t)(y / fy) * MX;
             int q = x0 / fx, r = x0 - q * fx;
+            if constexpr (std::is_same<T, uint8_t>::value && std::is_same<M, uint8_t>::value) {
+              if ((fx & 3) == 0) {
+                // four voxels of a 32-bit word share one mask value: two 16-bit lanes per multiply, each byte modulo 256
+                // (255 * 255 < 2^16: no carry between lanes) -- the per-byte path is bound by integer instructions
+                uint32_t w[4];
+                memcpy(w, &pack[u], 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t m = __ldg(mrow + q);
+                  w[k] = (((w[k] & 0x00FF00FFu) * m) & 0x00FF00FFu) | ((((w[k] >> 8) & 0x00FF00FFu) * m & 0x00FF00FFu) << 8);
+                  r += 4;
+                  if (r == fx) { r = 0; ++q; }
+                }
+                memcpy(&pack[u], w, 16);
+                *reinterpret_cast<uint4*>(chunk + (cz * Y + y) * X + x0) = pack[u];
+                continue;
+              }
+            }
             T e[V];
             memcpy(e, &pack[u], 16);
             M m = __ldg(mrow + q);  // one mask load per run of fx voxels

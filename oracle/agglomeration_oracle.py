@@ -21,7 +21,7 @@ test or golden vector for this plugin.  This file restates waterz's published al
          closer to a corner -- the sequential code may also pick a neighbour of the SAME distance that happens to sit
          earlier in its queue.  The two agree wherever no plateau has interior voxels with such a choice: always for
          maps without exact ties (float32 network outputs), and for saturated regions (>= aff_threshold_high), which have
-         no corners and stay whole.  tests/test_agglomeration.py checks both statements.
+         no corners and stay whole.  tests/test_segmentation_agglomerate.py checks both statements.
   2. region graph = one edge per pair of touching fragments with the statistics of the affinities between them (waterz
      ``backend/region_graph.hpp`` + ``MeanAffinityProvider``): sum and count.  Sums are accumulated in 2^-30 fixed point
      (order independent, so that the device's atomics and this scan agree bit for bit); waterz adds float32 values in

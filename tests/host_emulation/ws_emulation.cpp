@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE: runs the device code of chunkflow_b200/csrc/watershed_kernels.cuh on the host, one "thread" (grid 1 x 1,
 // so every grid-stride loop walks the whole volume; atomics are plain read-modify-writes), so that the LOGIC of the
 // watershed / region-graph / relabel kernels is compared with oracle/agglomeration_oracle.py on machines without a GPU
-// (tests/test_agglomeration.py builds this file with g++).  Concurrency is what the `-m gpu` tests add.
+// (tests/test_segmentation_agglomerate.py builds this file with g++).  Concurrency is what the `-m gpu` tests add.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

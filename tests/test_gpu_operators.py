@@ -111,6 +111,14 @@ def test_operators_random_vs_oracle(seed):
         c = _dev(chunk, voxel_size=vs)
         _dev(mask, voxel_size=mvs).maskout(c)
         np.testing.assert_array_equal(c.to_chunk().array, OP.maskout(mask, mvs, chunk, vs))
+    # 16-byte aligned uint8 rows: the vector path, with the packed four-voxels-per-multiply form (x factor a multiple of 4, also
+    # one that is no power of two) and the per-voxel form (x factor 2, 3), full-range mask values (products wrap modulo 256)
+    for fx, mx in ((4, 12), (12, 4), (8, 2), (2, 24), (3, 16)):
+        big = rng.integers(0, 256, size=(3, 10, fx * mx), dtype=np.uint8)
+        mk = rng.integers(0, 256, size=(3, 5, mx), dtype=np.uint8)
+        c = _dev(big, voxel_size=(4, 4, 4))
+        _dev(mk, voxel_size=(4, 8, 4 * fx)).maskout(c)
+        np.testing.assert_array_equal(c.to_chunk().array, OP.maskout(mk, (4, 8, 4 * fx), big, (4, 4, 4)))
     for mode in ("xy", "z"):
         good = np.clip(aff, 0, 1)  # out-of-range casts are platform defined in numpy: compare where the reference is defined
         np.testing.assert_array_equal(_dev(good).quantize(mode).to_chunk().array, OP.quantize(good, mode))

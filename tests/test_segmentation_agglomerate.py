@@ -267,14 +267,15 @@ def test_device_agglomerate_plugin_and_cli_against_the_oracle():
     pipeline = ["create-chunk", "--size", "16", "64", "64", "--pattern", "sin",
                 "inference", "--input-patch-size", "8", "32", "32", "--output-patch-overlap", "2", "8", "8",
                 "--num-output-channels", "3", "--framework", "identity", "--batch-size", "4", "--mask-output-chunk"]
-    res = CliRunner().invoke(cli.main, pipeline, standalone_mode=False)
-    assert res.exception is None, res.output
-    affs = res.return_value[0]["chunk"]
     res = CliRunner().invoke(cli.main, pipeline + ["agglomerate", "--threshold", "0.4", "-o", "seg"], standalone_mode=False)
     assert res.exception is None, res.output
     task = res.return_value[0]
     assert "agglomerate" in task["log"]["timer"]
-    assert np.array_equal(np.asarray(task["seg"].array).astype(np.uint64), A.agglomerate(np.asarray(affs.array), 0.4))
+    # the oracle works on the affinity map of THIS task (the blend's float atomics differ in the last bit from run to run,
+    # and on a map full of ties that moves watershed boundaries)
+    affs = np.asarray(task["chunk"].array)
+    assert affs.shape == (3, 16, 64, 64)
+    assert np.array_equal(np.asarray(task["seg"].array).astype(np.uint64), A.agglomerate(affs, 0.4))
 
 
 @pytest.mark.gpu

@@ -4,7 +4,7 @@ bound; algorithmic bytes per voxel: watershed = 12 B affinities + ~45 B of label
 8 B per breadth-first level; region graph = 12 B affinities + 4 B fragment ids (+ 16 B neighbour ids served by L2); relabel = 8 B.
 One JSON line.
 
-    python tools/bench_agglomerate.py [--size 256] [--z 128]
+    python tools/bench_agglomerate.py [--size 512] [--z 64]
 """
 import argparse
 import json
@@ -26,7 +26,7 @@ def smooth_affinities(z, n, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     a = torch.randn((3, 1, z, n, n), device="cuda", generator=g)
     k = torch.ones((1, 1, 3, 7, 7), device="cuda") / (3 * 7 * 7)
-    for _ in range(2):
+    for _ in range(4):
         a = torch.nn.functional.conv3d(a, k, padding=(1, 3, 3))
     a = a[:, 0]
     return torch.sigmoid(6.0 * a / a.std()).contiguous()
@@ -35,7 +35,7 @@ def smooth_affinities(z, n, seed=0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--z", type=int, default=128)
+    ap.add_argument("--z", type=int, default=64)
     ap.add_argument("--threshold", type=float, default=0.5)
     args = ap.parse_args()
     n, z = args.size, args.z
@@ -47,8 +47,8 @@ def main():
     dev = DeviceChunk(smooth_affinities(z, n), layer_type="affinity_map")
     vox = float(z) * n * n
 
-    def timed(fn, reps=3):
-        out = fn()   # warm-up
+    def timed(fn, reps=3, warm=True):
+        out = fn() if warm else None
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(reps):
@@ -59,8 +59,8 @@ def main():
     frag, ms_ws = timed(lambda: dev.watershed())
     (u, v, s, c), ms_rg = timed(lambda: dev.region_graph(frag))
     num = frag.num_components
-    root, ms_merge = timed(lambda: _native.agglomerate_edges_host(num + 1, u, v, s, c, args.threshold))
-    seg, ms_all = timed(lambda: dev.agglomerate(threshold=args.threshold))
+    root, ms_merge = timed(lambda: _native.agglomerate_edges_host(num + 1, u, v, s, c, args.threshold), reps=1, warm=False)
+    seg, ms_all = timed(lambda: dev.agglomerate(threshold=args.threshold), reps=1, warm=False)
     out = {"operator": "agglomerate", "volume": f"3x{z}x{n}x{n} float32", "threshold": args.threshold, "hbm_peak_gbs": peak,
            "fragments": int(num), "edges": int(u.size), "segments": int(seg.num_components),
            "watershed_ms": ms_ws, "watershed_mvoxels_per_s": vox / ms_ws / 1e3, "watershed_algorithmic_gbs": 57 * vox / ms_ws / 1e6,

@@ -22,6 +22,7 @@
 
 #include "chunkflow_b200.h"
 #include "common.cuh"
+#include "edge_sort.h"
 
 namespace cfb {
 namespace {
@@ -372,9 +373,8 @@ extern "C" int cfb_region_graph_read(void* d_workspace, int64_t table_slots, int
     CFB_CUDA(cudaMemcpyAsync(ct.data(), ocounts, (size_t)num_edges * 4, cudaMemcpyDeviceToHost, s));
     CFB_CUDA(cudaStreamSynchronize(s));
     if ((int64_t)got != num_edges) throw std::invalid_argument("region graph read: num_edges does not match the table");
-    std::vector<uint32_t> order((size_t)num_edges);
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return k[a] < k[b]; });   // the gather order is arbitrary
+    std::vector<uint32_t> order;
+    sorted_edge_order(k.data(), k.size(), order);   // the gather order is arbitrary
     for (size_t i = 0; i < order.size(); ++i) {
       const uint32_t o = order[i];
       h_u[i] = (uint32_t)(k[o] >> 32);

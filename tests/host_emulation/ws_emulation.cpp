@@ -25,6 +25,7 @@ using std::min;
 struct Int3 { int z, y, x; };
 constexpr int kT = 256;
 #include "../../chunkflow_b200/csrc/watershed_kernels.cuh"
+#include "../../chunkflow_b200/csrc/edge_sort.h"
 
 static WsGeom geom(int64_t z, int64_t y, int64_t x) {
   WsGeom g;
@@ -65,9 +66,8 @@ extern "C" int64_t emu_region_graph(const float* affs, int flip, const uint32_t*
   if (info[1]) return -1;
   rg_gather_kernel(keys.data(), sums.data(), counts.data(), slots, okeys.data(), osums.data(), ocounts.data(), &info[2]);
   if (info[2] != info[0]) return -2;
-  std::vector<uint32_t> order(info[0]);
-  for (uint32_t i = 0; i < info[0]; ++i) order[i] = i;
-  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return okeys[a] < okeys[b]; });
+  std::vector<uint32_t> order;
+  sorted_edge_order(okeys.data(), info[0], order);   // the product's host helper (csrc/edge_sort.h)
   for (uint32_t i = 0; i < info[0]; ++i) {
     const uint32_t o = order[i];
     u[i] = (uint32_t)(okeys[o] >> 32); v[i] = (uint32_t)(okeys[o] & 0xFFFFFFFFULL); sum_fixed[i] = osums[o]; count[i] = ocounts[o];

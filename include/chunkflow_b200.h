@@ -284,9 +284,9 @@ int cfb_region_graph_read(void* d_workspace, int64_t table_slots, int64_t num_ed
                           uint64_t* h_sum_fixed, uint32_t* h_count, void* stream);
 
 /* The merge loop (waterz backend/IterativeRegionMerging.hpp, scoring function OneMinus<MeanAffinity>), on the HOST like
- * waterz's own: repeatedly merge the edge with the smallest score 1 - sum / (count * 2^30) (ties: smaller ids first) until
- * the smallest score reaches `threshold`; the larger id is merged into the smaller one, edges to a common neighbour pool
- * their statistics.  root_of[i], i < num_nodes (= largest fragment id + 1), receives the id node i ends up with
+ * waterz's own: repeatedly merge the edge with the smallest score 1 - sum / (count * 2^30) (ties: the edge holding the smallest
+ * original (u, v) pair first) until the smallest score reaches `threshold`; a merged cluster is known by its smallest id,
+ * edges to a common neighbour pool their statistics.  root_of[i], i < num_nodes (= largest fragment id + 1), receives the id node i ends up with
  * (root_of[0] == 0).  No GPU involved. */
 int cfb_agglomerate_edges_host(int64_t num_nodes, int64_t num_edges, const uint32_t* u, const uint32_t* v,
                                const uint64_t* sum_fixed, const uint32_t* count, float threshold, uint32_t* root_of);

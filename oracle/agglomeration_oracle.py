@@ -27,9 +27,10 @@ test or golden vector for this plugin.  This file restates waterz's published al
      (order independent, so that the device's atomics and this scan agree bit for bit); waterz adds float32 values in
      scan order -- the means differ by rounding only.
   3. agglomeration = waterz ``IterativeRegionMerging``: merge the edge of the lowest score ``1 - mean affinity`` until
-     the lowest score reaches the threshold; merged regions pool the statistics of their edges.  Ties are broken by
-     (score, smaller id, larger id); the merged region keeps the smaller id (waterz keeps one of the two ids as well;
-     which one is not part of its published interface).  The result is NOT renumbered (neither is waterz's).
+     the lowest score reaches the threshold; merged regions pool the statistics of their edges.  Equal scores are taken
+     in the order of the smallest ORIGINAL fragment pair pooled into the edge (waterz: the order its heap happens to hold,
+     not part of its published interface); the merged region keeps the smaller id (waterz keeps one of the two ids as
+     well).  The result is NOT renumbered (neither is waterz's).
 """
 import heapq
 
@@ -263,38 +264,44 @@ def score(sum_fixed: int, count: int) -> float:
 
 
 def agglomerate_edges(num_nodes: int, u, v, sum_fixed, count, threshold: float) -> np.ndarray:
-    """root_of (num_nodes,) uint32: the id every node ends up with (0 stays 0)."""
+    """root_of (num_nodes,) uint32: the id every node ends up with (0 stays 0).
+
+    Every edge carries an ANCHOR: the smallest (u, v) pair of ORIGINAL fragments among the faces pooled into it.  The queue is
+    ordered by (score, anchor): among equal scores the edge holding the smallest original fragment pair goes first -- a rule
+    that does not depend on how an implementation stores clusters or which side of a merge it relabels (the native library
+    moves the SHORTER adjacency list; this restatement always moves the larger id's)."""
     adj = [dict() for _ in range(num_nodes)]
     heap = []
     for a, b, s, c in zip(np.asarray(u).tolist(), np.asarray(v).tolist(), np.asarray(sum_fixed).tolist(), np.asarray(count).tolist()):
         a, b = min(a, b), max(a, b)
-        adj[a][b] = (s, c)
-        adj[b][a] = (s, c)
-        heap.append((score(s, c), a, b, s, c))
+        anchor = (a << 32) | b
+        adj[a][b] = (s, c, anchor)
+        adj[b][a] = (s, c, anchor)
+        heap.append((score(s, c), anchor, a, b, s, c))
     heapq.heapify(heap)
     alive = [True] * num_nodes
     parent = list(range(num_nodes))
     thr = float(np.float32(threshold))
     while heap:
-        sc, a, b, s, c = heapq.heappop(heap)
-        if not (alive[a] and alive[b]) or adj[a].get(b) != (s, c):
+        sc, anchor, a, b, s, c = heapq.heappop(heap)
+        if not (alive[a] and alive[b]) or adj[a].get(b) != (s, c, anchor):
             continue   # stale
         if not sc < thr:
             break
-        # b (the larger id) is merged into a
+        # b (the larger id) is merged into a: the cluster keeps its smallest id
         alive[b] = False
         parent[b] = a
         del adj[a][b]
-        for n, (sn, cn) in adj[b].items():
+        for n, (sn, cn, an) in adj[b].items():
             if n == a:
                 continue
             del adj[n][b]
             if n in adj[a]:
-                so, co = adj[a][n]
-                sn, cn = sn + so, cn + co
-            adj[a][n] = (sn, cn)
-            adj[n][a] = (sn, cn)
-            heapq.heappush(heap, (score(sn, cn), min(a, n), max(a, n), sn, cn))
+                so, co, ao = adj[a][n]
+                sn, cn, an = sn + so, cn + co, min(an, ao)
+            adj[a][n] = (sn, cn, an)
+            adj[n][a] = (sn, cn, an)
+            heapq.heappush(heap, (score(sn, cn), an, min(a, n), max(a, n), sn, cn))
         adj[b] = {}
     out = np.zeros(num_nodes, np.uint32)
     for i in range(num_nodes):

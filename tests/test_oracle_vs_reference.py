@@ -107,3 +107,36 @@ def test_network_test_time_augmentation_literal(ref, unet_model):
     np.testing.assert_allclose(r.array, o, rtol=0, atol=1e-7)
     # ... and equals 1/4 (n(x) + rev_c n(x) + T n(T x) + rev_c T n(T x)): symmetric under channel reversal
     np.testing.assert_allclose(o[0], o[2], rtol=0, atol=1e-6)   # up to the order of the 8-term fp32 sum
+
+
+def test_patch_mask_random_geometries_reference_native_oracle(ref):
+    """PatchMask of the REAL reference (patch/patch_mask.py:6-68) == the native library's host code (`cfb_make_patch_mask`)
+    == the oracle, bit for bit, on 60 random patch sizes / overlaps (rows a3 / a4)."""
+    from chunkflow_b200 import _native
+    _, _, PatchMask = ref
+    rng = np.random.default_rng(2026)
+    for _ in range(60):
+        ps = tuple(int(v) for v in rng.integers(2, 40, 3))
+        ov = tuple(int(rng.integers(0, p // 2 + 1)) for p in ps)
+        want = np.asarray(PatchMask(ps, ov))
+        assert np.array_equal(_native.make_patch_mask(ps, ov), want), (ps, ov)
+        assert np.array_equal(O.make_patch_mask(ps, ov), want), (ps, ov)
+
+
+def test_identity_random_geometries_oracle_equals_reference(ref):
+    """Whole-operator arithmetic (patch grid with clamped last patches, blend order, chunk mask, normalise) on random small
+    chunk / patch / overlap combinations, identity backend: oracle == real reference, bit for bit (rows a1, a2, a5-a7, a11-a13)."""
+    rng = np.random.default_rng(7)
+    done = 0
+    while done < 12:
+        ps = tuple(int(v) for v in rng.integers(4, 13, 3))
+        ov = tuple(int(rng.integers(1, p // 2 + 1)) for p in ps)
+        size = tuple(int(p + rng.integers(0, 2 * p)) for p in ps)
+        img = rng.integers(1, 255, size=size, dtype=np.uint8)
+        off = tuple(int(v) for v in rng.integers(-5, 6, 3))
+        kw = dict(input_patch_size=ps, output_patch_overlap=ov, num_output_channels=int(rng.integers(1, 4)))
+        r = _run_ref(ref, img, offset=off, batch_size=int(rng.integers(1, 4)), framework="identity", mask_output_chunk=True, **kw)
+        o, o_off = O.infer_chunk(img, voxel_offset=off, framework="identity", **kw)
+        assert np.array_equal(np.asarray(r.array), o), (ps, ov, size)
+        assert tuple(r.voxel_offset) == tuple(o_off)
+        done += 1

@@ -188,6 +188,37 @@ def test_native_merge_loop_against_the_oracle():
         _native.agglomerate_edges_host(3, [1, 1], [2, 2], [1, 1], [1, 1], 0.5)   # duplicate edge
 
 
+def test_native_merge_loop_fuzz_shapes_ties_and_odd_thresholds():
+    """Random, chain, star + ring and dense graphs with few distinct means (ties everywhere), means above 1 (negative scores),
+    thresholds 0 / 1 / 2 / negative / inf: the native loop (bucket queue, shorter list moved) == the oracle's heap walk."""
+    from chunkflow_b200 import _native
+    rng = np.random.default_rng(123)
+    for t in range(160):
+        n = int(rng.integers(2, 40))
+        kind = t % 4
+        pairs = set()
+        if kind == 0:
+            for _ in range(int(rng.integers(0, n * 3))):
+                a, b = (int(x) for x in rng.integers(1, n, 2))
+                if a != b:
+                    pairs.add((min(a, b), max(a, b)))
+        elif kind == 1:
+            pairs = {(i, i + 1) for i in range(1, n - 1)}
+        elif kind == 2:
+            pairs = {(1, i) for i in range(2, n)} | {(i, i + 1) for i in range(2, n - 1)}
+        else:
+            pairs = {(a, b) for a in range(1, n) for b in range(a + 1, n) if rng.random() < 0.5}
+        pairs = sorted(pairs)
+        u = np.array([p for p, _ in pairs], np.uint32)
+        v = np.array([q for _, q in pairs], np.uint32)
+        c = rng.integers(1, 4, len(u)).astype(np.uint32)
+        levels = int(rng.choice([2, 3, 5, 1000]))
+        mean = rng.integers(0, levels + 1, len(u)) / levels * float(rng.choice([1.0, 1.0, 1.3]))
+        s = np.rint(mean * c * (1 << 30)).astype(np.uint64)
+        for thr in (float(rng.random()), 0.0, 1.0, 2.0, -0.5, float("inf")):
+            assert np.array_equal(_native.agglomerate_edges_host(n, u, v, s, c, thr), A.agglomerate_edges(n, u, v, s, c, thr)), (t, thr)
+
+
 def test_plugin_refuses_other_scoring_functions_and_needs_a_gpu():
     from chunkflow_b200 import Chunk
     from chunkflow_b200.plugins import agglomerate

@@ -13,24 +13,28 @@
 // Neither the order nor the result depends on which cluster's edges are MOVED, so the loop moves the shorter adjacency list
 // (every edge is moved O(log n) times instead of once per merge of its cluster).
 //
-// Data structures (the loop is memory-latency bound; one host core, 2.4 M fragments / 11.2 M edges of a noisy 64x512x512 map,
-// threshold 0.5, 1.8 M merges: 42 s with std::unordered_map, one std::vector per node and one binary heap; see
-// profiles/r02c_host_merge_loop.txt for the steps down from there):
+// Two phases, same result (tests run each alone and mixed against the oracle):
+//   1. ROUNDS of mutual-best merges on the sorted edge list (`mutual_best_rounds`): streaming passes, 1.5-4 us per merge, as
+//      long as a round merges enough to pay for its passes; clusters without an edge below the threshold are dropped with
+//      all their edges on the way (they can never merge nor influence a merge);
+//   2. the sequential WALK on what is left (`sequential_merge`): lowest (score, anchor) first.  Its data structures:
 //   * edges: ONE open-addressing table, key = (smaller id << 32 | larger id), linear probing, tombstones; pooled edges
 //     never outnumber the initial ones, so the table is sized once and only rebuilt when tombstones pile up;
-//   * clusters: a structural root (the node whose lists are alive) and a label (the smallest fragment id in it); the edge
-//     table and the queue use structural ids, the caller sees labels;
+//   * clusters: a structural root (the node whose lists are alive) and a label (the smallest fragment id in it);
 //   * adjacency: the initial neighbours of a node are one contiguous run (CSR) -- when the node is merged away, the table
 //     slots of all its edges (and of the edges they pool with) are prefetched before the first is touched --; neighbours a
 //     node gains through merges go to a linked overflow list; entries whose edge is gone are skipped lazily; the cluster
 //     with FEWER list entries is the one merged away;
-//   * priority queue: only edges with score < threshold ever enter it (the loop stops at the first score >= threshold, so
-//     entries at or above it can never be popped).  The mean of pooled edges lies between the means pooled, i.e. a new
-//     entry never scores below the edge being merged: the queue is MONOTONE, so 65 536 score buckets replace the global heap
-//     -- append-only vectors, and a small heap (a few hundred entries, cache resident) for the bucket being drained, which
+//   * priority queue: only edges with score < threshold ever enter it.  A new entry never precedes the edge being merged, so
+//     the queue is MONOTONE: 65 536 score buckets (append-only vectors) and a small heap for the bucket being drained, which
 //     keeps the exact (score, anchor) order inside it.
+// One host core, 2.4 M fragments / 11.2 M edges of a noisy 64x512x512 map, threshold 0.5, 1.8 M merges
+// (profiles/r02c_host_merge_loop.txt): 42 s with std::unordered_map + std::vector per node + one binary heap, 11.2 s for the
+// walk alone as it is now, 5.8 s with the rounds in front.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <queue>
 #include <stdexcept>
 #include <vector>
@@ -172,8 +176,225 @@ class BucketQueue {
   std::priority_queue<Entry, std::vector<Entry>, Later> heap_;
 };
 
+struct EdgeRec {   // one undirected edge between two clusters, named by their labels (the smallest fragment id of each)
+  uint64_t key;     // (smaller label << 32 | larger label)
+  uint64_t sum;
+  uint64_t anchor;
+  uint32_t count;
+  uint32_t mark;
+};
+
+// The sequential walk: lowest (score, anchor) first until the threshold.  `root[i]` (identity on entry) receives, for
+// every node that is an endpoint in E or not, the label of the cluster it ends in.
+void sequential_merge(int64_t num_nodes, const std::vector<EdgeRec>& E, double thr, std::vector<uint32_t>& root) {
+  const size_t num_edges = E.size();
+  EdgeTable edges(num_edges);
+  // initial adjacency as CSR; neighbours gained later in an overflow list per node
+  std::vector<uint32_t> adj_start((size_t)num_nodes + 1, 0), adj(num_edges * 2);
+  for (const EdgeRec& e : E) {
+    ++adj_start[(size_t)(e.key >> 32) + 1];
+    ++adj_start[(size_t)(e.key & 0xFFFFFFFFu) + 1];
+  }
+  for (int64_t i = 0; i < num_nodes; ++i) adj_start[i + 1] += adj_start[i];
+  {
+    std::vector<uint32_t> cursor(adj_start.begin(), adj_start.end() - 1);
+    for (const EdgeRec& e : E) {
+      const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
+      adj[cursor[a]++] = b;
+      adj[cursor[b]++] = a;
+    }
+  }
+  std::vector<uint32_t> head((size_t)num_nodes, kNil);
+  std::vector<Link> pool;
+  auto link = [&](uint32_t from, uint32_t to) {
+    pool.push_back(Link{to, head[from]});
+    head[from] = (uint32_t)(pool.size() - 1);
+  };
+  std::vector<Entry> initial;
+  double lowest = thr;
+  for (const EdgeRec& e : E) {
+    edges.insert(e.key, e.sum, e.anchor, e.count);
+    const double sc = edge_score(e.sum, e.count);
+    if (sc < thr) {
+      initial.push_back(Entry{sc, e.anchor, e.sum, (uint32_t)(e.key >> 32), (uint32_t)e.key, e.count});
+      if (sc < lowest) lowest = sc;
+    }
+  }
+  BucketQueue queue(lowest, thr, std::move(initial));
+  std::vector<uint8_t> alive((size_t)num_nodes, 1);
+  std::vector<uint32_t> parent((size_t)num_nodes), label((size_t)num_nodes), entries((size_t)num_nodes);
+  for (int64_t i = 0; i < num_nodes; ++i) {
+    parent[i] = label[i] = (uint32_t)i;
+    entries[i] = adj_start[i + 1] - adj_start[i];   // list entries (CSR run + overflow), dead ones included
+  }
+  Entry e;
+  while (queue.pop(e)) {
+    if (!alive[e.a] || !alive[e.b]) continue;
+    EdgeTable::Slot* it = edges.find(edge_key(e.a, e.b));
+    if (!it || it->sum != e.sum || it->count != e.count) continue;  // superseded entry
+    // (every entry in the queue has score < threshold: nothing to test here; the loop ends when the queue runs dry)
+    // the cluster with fewer list entries is merged away (`gone`) into the other (`keep`); equal: the larger root goes
+    const bool a_goes = entries[e.a] < entries[e.b] || (entries[e.a] == entries[e.b] && e.a > e.b);
+    const uint32_t keep = a_goes ? e.b : e.a, gone = a_goes ? e.a : e.b;
+    alive[gone] = 0;
+    parent[gone] = keep;
+    if (label[gone] < label[keep]) label[keep] = label[gone];
+    edges.erase(it);
+    auto visit = [&](uint32_t n) {
+      if (n == keep || !alive[n]) return;
+      EdgeTable::Slot* eg = edges.find(edge_key(gone, n));
+      if (!eg) return;  // an entry left behind by an earlier merge
+      uint64_t sum = eg->sum, anchor = eg->anchor;
+      uint32_t cnt = eg->count;
+      edges.erase(eg);
+      if (EdgeTable::Slot* ek = edges.find(edge_key(keep, n))) {
+        sum += ek->sum;
+        cnt += ek->count;
+        if (ek->anchor < anchor) anchor = ek->anchor;
+        ek->sum = sum;
+        ek->count = cnt;
+        ek->anchor = anchor;
+      } else {
+        edges.insert(edge_key(keep, n), sum, anchor, cnt);
+        link(keep, n);
+        link(n, keep);
+        ++entries[keep];
+        ++entries[n];
+      }
+      const double sc = edge_score(sum, cnt);
+      if (sc < thr) queue.push(Entry{sc, anchor, sum, keep, n, cnt});
+    };
+    const uint32_t lo = adj_start[gone], hi = adj_start[gone + 1];
+    for (uint32_t i = lo; i < hi; ++i) {   // all the cache misses of this merge in flight at once
+      const uint32_t n = adj[i];
+      edges.prefetch(edge_key(gone, n));
+      edges.prefetch(edge_key(keep, n));
+      __builtin_prefetch(&head[n]);
+    }
+    for (uint32_t i = lo; i < hi; ++i) visit(adj[i]);
+    for (uint32_t l = head[gone]; l != kNil;) {
+      const Link lk = pool[l];   // (pool may grow in visit(): copy, do not hold a reference)
+      l = lk.next;
+      visit(lk.node);
+    }
+    head[gone] = kNil;
+  }
+  for (int64_t i = 0; i < num_nodes; ++i) {
+    uint32_t r = (uint32_t)i;
+    while (parent[r] != r) r = parent[r];
+    for (uint32_t c = (uint32_t)i; parent[c] != r;) { const uint32_t nx = parent[c]; parent[c] = r; c = nx; }  // compress
+    root[i] = label[r];
+  }
+}
+
+// Rounds of mutual-best merges on the sorted edge list.  (score, anchor) is a strict total order that moving an edge never
+// changes, and a pooled edge never precedes both edges pooled (its score lies between theirs, its anchor is the smaller one):
+// two clusters that are each other's best edge below the threshold stay so whatever merges elsewhere, so the sequential walk
+// merges exactly them sooner or later -- all such pairs of a round are merged at once.  One round = streaming passes:
+// best edge per cluster, mark the mutual ones, rename the absorbed clusters in the edges that touch them, sort those edges and
+// merge them back into the (still sorted) rest, pooling equal keys; edges of clusters that have no edge below the threshold
+// are dropped on the way (they can never matter).  When a round merges too little to pay for its passes, the sequential walk
+// finishes on what is left.  `parent` is the union forest over fragment ids
+// (always larger id -> smaller id, so a root is its cluster's label).
+// returns the number of rounds run
+constexpr double kWalkSecondsPerMerge = 4e-6;
+
+int mutual_best_rounds(int64_t num_nodes, std::vector<EdgeRec>& E, double thr, std::vector<uint32_t>& parent, int mode) {
+  struct Best { double score; uint64_t anchor; uint32_t idx; };
+  std::vector<Best> best((size_t)num_nodes);
+  std::vector<EdgeRec> moved, merged;
+  int rounds = 0;
+  for (;;) {
+    if (E.empty()) break;
+    if (mode != 2 && (E.size() < 4096)) break;            // small graphs: the sequential walk is quicker than more passes
+    // best edge below the threshold of every cluster
+    for (const EdgeRec& e : E) {
+      best[(size_t)(e.key >> 32)].idx = kNil;
+      best[(size_t)(e.key & 0xFFFFFFFFu)].idx = kNil;
+    }
+    for (size_t i = 0; i < E.size(); ++i) {
+      const EdgeRec& e = E[i];
+      const double sc = edge_score(e.sum, e.count);
+      if (!(sc < thr)) continue;
+      for (int side = 0; side < 2; ++side) {
+        Best& b = best[side ? (size_t)(e.key & 0xFFFFFFFFu) : (size_t)(e.key >> 32)];
+        if (b.idx == kNil || sc < b.score || (sc == b.score && e.anchor < b.anchor)) b = Best{sc, e.anchor, (uint32_t)i};
+      }
+    }
+    // mutual pairs: the larger label is absorbed by the smaller
+    const auto t_round = std::chrono::steady_clock::now();
+    size_t merges = 0;
+    for (size_t i = 0; i < E.size(); ++i) {
+      EdgeRec& e = E[i];
+      const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
+      e.mark = 0;
+      if (best[a].idx == (uint32_t)i && best[b].idx == (uint32_t)i) {
+        e.mark = 1;
+        parent[b] = a;
+        ++merges;
+      }
+    }
+    if (!merges) {   // nothing mutual (then nothing is below the threshold at all): only the pruning is left to do
+      size_t kept = 0;
+      for (size_t i = 0; i < E.size(); ++i) {
+        const uint32_t a = (uint32_t)(E[i].key >> 32), b = (uint32_t)E[i].key;
+        if (best[a].idx != kNil && best[b].idx != kNil) E[kept++] = E[i];
+      }
+      E.resize(kept);
+      break;
+    }
+    ++rounds;
+    // rename: only edges that touch an absorbed cluster change (parent[x] != x exactly for the clusters absorbed this round:
+    // every endpoint of E was a root when the round began)
+    moved.clear();
+    size_t kept = 0, pruned = 0;
+    for (size_t i = 0; i < E.size(); ++i) {
+      const EdgeRec& e = E[i];
+      if (e.mark) continue;   // the merged edge itself disappears
+      const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
+      // A cluster without an edge below the threshold never gets one (its edges only ever pool with each other, and a pooled
+      // score is no smaller than the smaller one pooled) and never merges: its edges cannot influence anything -- dropped.
+      if (best[a].idx == kNil || best[b].idx == kNil) { ++pruned; continue; }
+      const uint32_t na = parent[a], nb = parent[b];
+      if (na == a && nb == b) { E[kept++] = e; continue; }
+      EdgeRec m = e;
+      m.key = edge_key(na, nb);
+      moved.push_back(m);
+    }
+    E.resize(kept);
+    std::sort(moved.begin(), moved.end(), [](const EdgeRec& x, const EdgeRec& y) { return x.key < y.key; });
+    // merge the two sorted runs, pooling equal keys (an edge can meet its twin in the other run or in its own)
+    merged.clear();
+    merged.reserve(E.size() + moved.size());
+    auto emit = [&](const EdgeRec& r) {
+      if (!merged.empty() && merged.back().key == r.key) {
+        EdgeRec& t = merged.back();
+        t.sum += r.sum;
+        t.count += r.count;
+        if (r.anchor < t.anchor) t.anchor = r.anchor;
+      } else {
+        merged.push_back(r);
+      }
+    };
+    size_t i = 0, j = 0;
+    while (i < E.size() || j < moved.size()) {
+      if (j == moved.size() || (i < E.size() && E[i].key <= moved[j].key)) emit(E[i++]);
+      else emit(moved[j++]);
+    }
+    E.swap(merged);
+    (void)pruned;
+    // hand over to the sequential walk when a round costs more than the walk would for the same merges (the walk moves
+    // every edge of a merged cluster through a hash table: a few microseconds per merge; the result does not depend on
+    // where the hand-over happens)
+    const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_round).count();
+    if (mode != 2 && seconds > (double)merges * kWalkSecondsPerMerge) break;
+  }
+  return rounds;
+}
+
 }  // namespace
 
+// CFB_AGGLOMERATE_MODE (development / tests): 0 = sequential walk only, 1 = rounds, then the walk (default), 2 = rounds until none merges, then the walk
 extern "C" int cfb_agglomerate_edges_host(int64_t num_nodes, int64_t num_edges, const uint32_t* u, const uint32_t* v,
                                           const uint64_t* sum_fixed, const uint32_t* count, float threshold, uint32_t* root_of) {
   try {
@@ -181,103 +402,31 @@ extern "C" int cfb_agglomerate_edges_host(int64_t num_nodes, int64_t num_edges, 
       throw std::invalid_argument("agglomerate: bad sizes");
     if (num_edges && (!u || !v || !sum_fixed || !count)) throw std::invalid_argument("agglomerate: null edge arrays");
     const double thr = (double)threshold;
-    EdgeTable edges((size_t)num_edges);
-    // initial adjacency as CSR; neighbours gained later in an overflow list per node
-    std::vector<uint32_t> adj_start((size_t)num_nodes + 1, 0), adj((size_t)num_edges * 2);
+    int mode = 1;
+    if (const char* m = std::getenv("CFB_AGGLOMERATE_MODE")) mode = std::atoi(m);
+    std::vector<EdgeRec> E((size_t)num_edges);
+    bool sorted = true;
     for (int64_t i = 0; i < num_edges; ++i) {
       if (u[i] >= num_nodes || v[i] >= num_nodes || u[i] == v[i] || !count[i])
         throw std::invalid_argument("agglomerate: edge with an id outside [0, num_nodes), a self loop or a zero count");
-      ++adj_start[(size_t)u[i] + 1];
-      ++adj_start[(size_t)v[i] + 1];
+      const uint64_t key = edge_key(u[i], v[i]);
+      E[(size_t)i] = EdgeRec{key, sum_fixed[i], key, count[i], 0};
+      if (i && key < E[(size_t)i - 1].key) sorted = false;
     }
-    for (int64_t i = 0; i < num_nodes; ++i) adj_start[i + 1] += adj_start[i];
-    {
-      std::vector<uint32_t> cursor(adj_start.begin(), adj_start.end() - 1);
-      for (int64_t i = 0; i < num_edges; ++i) { adj[cursor[u[i]]++] = v[i]; adj[cursor[v[i]]++] = u[i]; }
-    }
-    std::vector<uint32_t> head((size_t)num_nodes, kNil);
-    std::vector<Link> pool;
-    auto link = [&](uint32_t from, uint32_t to) {
-      pool.push_back(Link{to, head[from]});
-      head[from] = (uint32_t)(pool.size() - 1);
-    };
-    std::vector<Entry> initial;
-    double lowest = thr;
-    for (int64_t i = 0; i < num_edges; ++i) {
-      const uint32_t a = u[i] < v[i] ? u[i] : v[i], b = u[i] < v[i] ? v[i] : u[i];
-      const uint64_t key = edge_key(a, b);
-      if (edges.find(key)) throw std::invalid_argument("agglomerate: duplicate edge");
-      edges.insert(key, sum_fixed[i], key, count[i]);
-      const double sc = edge_score(sum_fixed[i], count[i]);
-      if (sc < thr) {
-        initial.push_back(Entry{sc, key, sum_fixed[i], a, b, count[i]});
-        if (sc < lowest) lowest = sc;
-      }
-    }
-    BucketQueue queue(lowest, thr, std::move(initial));
-    std::vector<uint8_t> alive((size_t)num_nodes, 1);
-    std::vector<uint32_t> parent((size_t)num_nodes), label((size_t)num_nodes), entries((size_t)num_nodes);
-    for (int64_t i = 0; i < num_nodes; ++i) {
-      parent[i] = label[i] = (uint32_t)i;
-      entries[i] = adj_start[i + 1] - adj_start[i];   // list entries (CSR run + overflow), dead ones included
-    }
-    Entry e;
-    while (queue.pop(e)) {
-      if (!alive[e.a] || !alive[e.b]) continue;
-      EdgeTable::Slot* it = edges.find(edge_key(e.a, e.b));
-      if (!it || it->sum != e.sum || it->count != e.count) continue;  // superseded entry
-      // (every entry in the queue has score < threshold: nothing to test here; the loop ends when the queue runs dry)
-      // the cluster with fewer list entries is merged away (`gone`) into the other (`keep`); equal: the larger root goes
-      const bool a_goes = entries[e.a] < entries[e.b] || (entries[e.a] == entries[e.b] && e.a > e.b);
-      const uint32_t keep = a_goes ? e.b : e.a, gone = a_goes ? e.a : e.b;
-      alive[gone] = 0;
-      parent[gone] = keep;
-      if (label[gone] < label[keep]) label[keep] = label[gone];
-      edges.erase(it);
-      auto visit = [&](uint32_t n) {
-        if (n == keep || !alive[n]) return;
-        EdgeTable::Slot* eg = edges.find(edge_key(gone, n));
-        if (!eg) return;  // an entry left behind by an earlier merge
-        uint64_t sum = eg->sum, anchor = eg->anchor;
-        uint32_t cnt = eg->count;
-        edges.erase(eg);
-        if (EdgeTable::Slot* ek = edges.find(edge_key(keep, n))) {
-          sum += ek->sum;
-          cnt += ek->count;
-          if (ek->anchor < anchor) anchor = ek->anchor;
-          ek->sum = sum;
-          ek->count = cnt;
-          ek->anchor = anchor;
-        } else {
-          edges.insert(edge_key(keep, n), sum, anchor, cnt);
-          link(keep, n);
-          link(n, keep);
-          ++entries[keep];
-          ++entries[n];
-        }
-        const double sc = edge_score(sum, cnt);
-        if (sc < thr) queue.push(Entry{sc, anchor, sum, keep, n, cnt});
-      };
-      const uint32_t lo = adj_start[gone], hi = adj_start[gone + 1];
-      for (uint32_t i = lo; i < hi; ++i) {   // all the cache misses of this merge in flight at once
-        const uint32_t n = adj[i];
-        edges.prefetch(edge_key(gone, n));
-        edges.prefetch(edge_key(keep, n));
-        __builtin_prefetch(&head[n]);
-      }
-      for (uint32_t i = lo; i < hi; ++i) visit(adj[i]);
-      for (uint32_t l = head[gone]; l != kNil;) {
-        const Link lk = pool[l];   // (pool may grow in visit(): copy, do not hold a reference)
-        l = lk.next;
-        visit(lk.node);
-      }
-      head[gone] = kNil;
-    }
+    if (!sorted) std::sort(E.begin(), E.end(), [](const EdgeRec& x, const EdgeRec& y) { return x.key < y.key; });
+    for (size_t i = 1; i < E.size(); ++i)
+      if (E[i].key == E[i - 1].key) throw std::invalid_argument("agglomerate: duplicate edge");
+    std::vector<uint32_t> parent((size_t)num_nodes);
+    for (int64_t i = 0; i < num_nodes; ++i) parent[i] = (uint32_t)i;
+    if (mode != 0) mutual_best_rounds(num_nodes, E, thr, parent, mode);
+    // the walk on what is left: cluster labels are node ids of the contracted graph
+    std::vector<uint32_t> root((size_t)num_nodes);
+    for (int64_t i = 0; i < num_nodes; ++i) root[i] = (uint32_t)i;
+    if (!E.empty()) sequential_merge(num_nodes, E, thr, root);
     for (int64_t i = 0; i < num_nodes; ++i) {
       uint32_t r = (uint32_t)i;
       while (parent[r] != r) r = parent[r];
-      for (uint32_t c = (uint32_t)i; parent[c] != r;) { const uint32_t nx = parent[c]; parent[c] = r; c = nx; }  // compress
-      root_of[i] = label[r];
+      root_of[i] = root[r];
     }
     return CFB_OK;
   } catch (const std::invalid_argument& ex) {

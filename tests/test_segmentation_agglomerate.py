@@ -156,10 +156,14 @@ def test_whole_operator_with_emulated_voxel_passes_and_the_native_merge_loop(emu
 # ------------------------------------------------------------------------------------------------------------
 # the host merge loop of the native library (no GPU involved)
 # ------------------------------------------------------------------------------------------------------------
-def test_native_merge_loop_against_the_oracle():
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_native_merge_loop_against_the_oracle(monkeypatch, mode):
     from chunkflow_b200 import _native
+    monkeypatch.setenv("CFB_AGGLOMERATE_MODE", mode)
     rng = np.random.default_rng(7)
-    for trial, (shape, thr, kind) in enumerate((((6, 10, 12), 0.5, 0), ((8, 12, 12), 0.3, 5), ((5, 9, 9), 0.8, 1), ((10, 16, 16), 0.45, 0))):
+    # (the last two graphs have more than 4096 edges: in mode 1 they go through rounds, pruning and the hand-over to the walk)
+    for trial, (shape, thr, kind) in enumerate((((6, 10, 12), 0.5, 0), ((8, 12, 12), 0.3, 5), ((5, 9, 9), 0.8, 1), ((10, 16, 16), 0.45, 0),
+                                                ((12, 28, 28), 0.5, 0), ((10, 30, 30), 0.35, 5))):
         a = _affinities(trial, shape, kind)
         frag = A.watershed(a, LOW, HIGH)
         u, v, s, c = A.region_graph(a, frag)
@@ -188,10 +192,14 @@ def test_native_merge_loop_against_the_oracle():
         _native.agglomerate_edges_host(3, [1, 1], [2, 2], [1, 1], [1, 1], 0.5)   # duplicate edge
 
 
-def test_native_merge_loop_fuzz_shapes_ties_and_odd_thresholds():
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+def test_native_merge_loop_fuzz_shapes_ties_and_odd_thresholds(monkeypatch, mode):
     """Random, chain, star + ring and dense graphs with few distinct means (ties everywhere), means above 1 (negative scores),
-    thresholds 0 / 1 / 2 / negative / inf: the native loop (bucket queue, shorter list moved) == the oracle's heap walk."""
+    thresholds 0 / 1 / 2 / negative / inf: the native loop == the oracle's heap walk, in each of its modes -- 0: the sequential
+    walk alone (bucket queue, shorter list moved), 2: rounds of mutual-best merges until none is left (on graphs of any size:
+    the reducibility argument put to the test, ties included), 1: the product's mix (rounds on large graphs, then the walk)."""
     from chunkflow_b200 import _native
+    monkeypatch.setenv("CFB_AGGLOMERATE_MODE", mode)
     rng = np.random.default_rng(123)
     for t in range(160):
         n = int(rng.integers(2, 40))

@@ -30,8 +30,13 @@
 //     keeps the exact (score, anchor) order inside it.
 // One host core, 2.4 M fragments / 11.2 M edges of a noisy 64x512x512 map, threshold 0.5, 1.8 M merges
 // (profiles/r02c_host_merge_loop.txt): 42 s with std::unordered_map + std::vector per node + one binary heap, 11.2 s for the
-// walk alone as it is now, 5.8 s with the rounds in front.
+// walk alone as it is now, 3.4 s with the rounds in front on 8 threads (the rounds share every pass among worker threads;
+// the walk is one thread).
 #include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <exception>
+#include <thread>
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
@@ -299,90 +304,193 @@ void sequential_merge(int64_t num_nodes, const std::vector<EdgeRec>& E, double t
 // returns the number of rounds run
 constexpr double kWalkSecondsPerMerge = 4e-6;   // measured break-even on the build box (the total is flat between 4 and 6 us)
 
-int mutual_best_rounds(int64_t num_nodes, std::vector<EdgeRec>& E, double thr, std::vector<uint32_t>& parent, int mode) {
-  struct Best { double score; uint64_t anchor; uint32_t idx; };
-  std::vector<Best> best((size_t)num_nodes);
-  std::vector<EdgeRec> moved, merged;
+// fork-join over `threads` workers: fn(t) for t in [0, threads); exceptions of the workers are rethrown
+template <typename F>
+void parallel_for(int threads, F&& fn) {
+  if (threads <= 1) { fn(0); return; }
+  std::vector<std::thread> pool;
+  std::vector<std::exception_ptr> errors((size_t)threads);
+  for (int t = 1; t < threads; ++t)
+    pool.emplace_back([&, t] { try { fn(t); } catch (...) { errors[(size_t)t] = std::current_exception(); } });
+  try { fn(0); } catch (...) { errors[0] = std::current_exception(); }
+  for (auto& th : pool) th.join();
+  for (auto& e : errors) if (e) std::rethrow_exception(e);
+}
+
+inline void atomic_min(std::atomic<uint64_t>& a, uint64_t v) {
+  uint64_t cur = a.load(std::memory_order_relaxed);
+  while (v < cur && !a.compare_exchange_weak(cur, v, std::memory_order_relaxed)) {}
+}
+
+// order-preserving image of a double in the unsigned integers (scores may be negative when a mean exceeds 1)
+inline uint64_t sortable(double d) {
+  uint64_t b;
+  std::memcpy(&b, &d, 8);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+// `threads` workers share every pass: contiguous slices of the edge list; the per-cluster minimum of (score, anchor) is taken
+// in three passes of atomic minima (score, then anchor among the edges that hold the score, then the index of the one edge
+// that holds both -- anchors are unique), so the outcome does not depend on the interleaving.
+int mutual_best_rounds(int64_t num_nodes, std::vector<EdgeRec>& E, double thr, std::vector<uint32_t>& parent, int mode, int threads,
+                       size_t grain) {
+  constexpr uint64_t kNone = ~0ULL;
+  std::vector<std::atomic<uint64_t>> bscore((size_t)num_nodes), banchor((size_t)num_nodes);
+  std::vector<std::atomic<uint32_t>> bidx((size_t)num_nodes);
+  std::vector<uint64_t> skey;
+  std::vector<EdgeRec> kept_buf;
+  std::vector<std::vector<EdgeRec>> moved((size_t)threads), out((size_t)threads), mine((size_t)threads);
+  std::vector<size_t> n_merge((size_t)threads), n_kept((size_t)threads);
   int rounds = 0;
   for (;;) {
     if (E.empty()) break;
     if (mode != 2 && (E.size() < 4096)) break;            // small graphs: the sequential walk is quicker than more passes
     const auto t_round = std::chrono::steady_clock::now();
+    const size_t n = E.size();
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, n / grain + 1));   // at least `grain` edges per worker
+    auto slice = [&](int t, size_t& lo, size_t& hi) { lo = n * (size_t)t / (size_t)T; hi = n * (size_t)(t + 1) / (size_t)T; };
+    skey.resize(n);
     // best edge below the threshold of every cluster
-    for (const EdgeRec& e : E) {
-      best[(size_t)(e.key >> 32)].idx = kNil;
-      best[(size_t)(e.key & 0xFFFFFFFFu)].idx = kNil;
-    }
-    for (size_t i = 0; i < E.size(); ++i) {
-      const EdgeRec& e = E[i];
-      const double sc = edge_score(e.sum, e.count);
-      if (!(sc < thr)) continue;
-      for (int side = 0; side < 2; ++side) {
-        Best& b = best[side ? (size_t)(e.key & 0xFFFFFFFFu) : (size_t)(e.key >> 32)];
-        if (b.idx == kNil || sc < b.score || (sc == b.score && e.anchor < b.anchor)) b = Best{sc, e.anchor, (uint32_t)i};
-      }
-    }
-    // mutual pairs: the larger label is absorbed by the smaller
-    size_t merges = 0;
-    for (size_t i = 0; i < E.size(); ++i) {
-      EdgeRec& e = E[i];
-      const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
-      e.mark = 0;
-      if (best[a].idx == (uint32_t)i && best[b].idx == (uint32_t)i) {
-        e.mark = 1;
-        parent[b] = a;
-        ++merges;
-      }
-    }
-    if (!merges) {   // nothing mutual (then nothing is below the threshold at all): only the pruning is left to do
-      size_t kept = 0;
-      for (size_t i = 0; i < E.size(); ++i) {
+    parallel_for(T, [&](int t) {
+      size_t lo, hi; slice(t, lo, hi);
+      for (size_t i = lo; i < hi; ++i) {
         const uint32_t a = (uint32_t)(E[i].key >> 32), b = (uint32_t)E[i].key;
-        if (best[a].idx != kNil && best[b].idx != kNil) E[kept++] = E[i];
+        bscore[a].store(kNone, std::memory_order_relaxed); bscore[b].store(kNone, std::memory_order_relaxed);
+        banchor[a].store(kNone, std::memory_order_relaxed); banchor[b].store(kNone, std::memory_order_relaxed);
+        bidx[a].store(kNil, std::memory_order_relaxed); bidx[b].store(kNil, std::memory_order_relaxed);
       }
-      E.resize(kept);
+    });
+    parallel_for(T, [&](int t) {
+      size_t lo, hi; slice(t, lo, hi);
+      for (size_t i = lo; i < hi; ++i) {
+        const double sc = edge_score(E[i].sum, E[i].count);
+        if (!(sc < thr)) { skey[i] = kNone; continue; }
+        const uint64_t k = sortable(sc);
+        skey[i] = k;
+        atomic_min(bscore[(size_t)(E[i].key >> 32)], k);
+        atomic_min(bscore[(size_t)(E[i].key & 0xFFFFFFFFu)], k);
+      }
+    });
+    parallel_for(T, [&](int t) {
+      size_t lo, hi; slice(t, lo, hi);
+      for (size_t i = lo; i < hi; ++i) {
+        if (skey[i] == kNone) continue;
+        const size_t a = (size_t)(E[i].key >> 32), b = (size_t)(E[i].key & 0xFFFFFFFFu);
+        if (bscore[a].load(std::memory_order_relaxed) == skey[i]) atomic_min(banchor[a], E[i].anchor);
+        if (bscore[b].load(std::memory_order_relaxed) == skey[i]) atomic_min(banchor[b], E[i].anchor);
+      }
+    });
+    parallel_for(T, [&](int t) {
+      size_t lo, hi; slice(t, lo, hi);
+      for (size_t i = lo; i < hi; ++i) {
+        if (skey[i] == kNone) continue;
+        const size_t a = (size_t)(E[i].key >> 32), b = (size_t)(E[i].key & 0xFFFFFFFFu);
+        if (bscore[a].load(std::memory_order_relaxed) == skey[i] && banchor[a].load(std::memory_order_relaxed) == E[i].anchor) bidx[a].store((uint32_t)i, std::memory_order_relaxed);
+        if (bscore[b].load(std::memory_order_relaxed) == skey[i] && banchor[b].load(std::memory_order_relaxed) == E[i].anchor) bidx[b].store((uint32_t)i, std::memory_order_relaxed);
+      }
+    });
+    // mutual pairs: the larger label is absorbed by the smaller (one edge per absorbed cluster: no two writers per entry)
+    parallel_for(T, [&](int t) {
+      size_t lo, hi; slice(t, lo, hi);
+      size_t m = 0;
+      for (size_t i = lo; i < hi; ++i) {
+        const uint32_t a = (uint32_t)(E[i].key >> 32), b = (uint32_t)E[i].key;
+        const bool mutual = bidx[a].load(std::memory_order_relaxed) == (uint32_t)i && bidx[b].load(std::memory_order_relaxed) == (uint32_t)i;
+        E[i].mark = mutual ? 1u : 0u;
+        if (mutual) { parent[b] = a; ++m; }
+      }
+      n_merge[(size_t)t] = m;
+    });
+    size_t merges = 0;
+    for (int t = 0; t < T; ++t) merges += n_merge[(size_t)t];
+    // rename: only edges that touch an absorbed cluster change (parent[x] != x exactly for the clusters absorbed this round:
+    // every endpoint of E was a root when the round began); the merged edges disappear; so do the edges of clusters without
+    // an edge below the threshold -- such a cluster never gets one (its edges only ever pool with each other, and a pooled
+    // score is no smaller than the smaller one pooled) and never merges: its edges cannot influence anything.
+    kept_buf.resize(n);
+    parallel_for(T, [&](int t) {   // pass 1: count the edges that stay as they are, collect (renamed, locally sorted) the others
+      size_t lo, hi; slice(t, lo, hi);
+      std::vector<EdgeRec>& mv = moved[(size_t)t];
+      mv.clear();
+      size_t k = 0;
+      for (size_t i = lo; i < hi; ++i) {
+        const EdgeRec& e = E[i];
+        if (e.mark) continue;
+        const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
+        if (bidx[a].load(std::memory_order_relaxed) == kNil || bidx[b].load(std::memory_order_relaxed) == kNil) continue;
+        const uint32_t na = parent[a], nb = parent[b];
+        if (na == a && nb == b) { ++k; continue; }
+        EdgeRec m = e;
+        m.key = edge_key(na, nb);
+        mv.push_back(m);
+      }
+      n_kept[(size_t)t] = k;
+      std::sort(mv.begin(), mv.end(), [](const EdgeRec& x, const EdgeRec& y) { return x.key < y.key; });
+    });
+    size_t total_kept = 0;
+    for (int t = 0; t < T; ++t) { const size_t k = n_kept[(size_t)t]; n_kept[(size_t)t] = total_kept; total_kept += k; }
+    parallel_for(T, [&](int t) {   // pass 2: the unchanged edges, compacted in order (still sorted)
+      size_t lo, hi; slice(t, lo, hi);
+      size_t k = n_kept[(size_t)t];
+      for (size_t i = lo; i < hi; ++i) {
+        const EdgeRec& e = E[i];
+        if (e.mark) continue;
+        const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
+        if (bidx[a].load(std::memory_order_relaxed) == kNil || bidx[b].load(std::memory_order_relaxed) == kNil) continue;
+        if (parent[a] == a && parent[b] == b) kept_buf[k++] = e;
+      }
+    });
+    if (!merges) {   // nothing mutual (then nothing is below the threshold at all): the pruning was all there was to do
+      kept_buf.resize(total_kept);
+      E.swap(kept_buf);
       break;
     }
     ++rounds;
-    // rename: only edges that touch an absorbed cluster change (parent[x] != x exactly for the clusters absorbed this round:
-    // every endpoint of E was a root when the round began)
-    moved.clear();
-    size_t kept = 0, pruned = 0;
-    for (size_t i = 0; i < E.size(); ++i) {
-      const EdgeRec& e = E[i];
-      if (e.mark) continue;   // the merged edge itself disappears
-      const uint32_t a = (uint32_t)(e.key >> 32), b = (uint32_t)e.key;
-      // A cluster without an edge below the threshold never gets one (its edges only ever pool with each other, and a pooled
-      // score is no smaller than the smaller one pooled) and never merges: its edges cannot influence anything -- dropped.
-      if (best[a].idx == kNil || best[b].idx == kNil) { ++pruned; continue; }
-      const uint32_t na = parent[a], nb = parent[b];
-      if (na == a && nb == b) { E[kept++] = e; continue; }
-      EdgeRec m = e;
-      m.key = edge_key(na, nb);
-      moved.push_back(m);
-    }
-    E.resize(kept);
-    std::sort(moved.begin(), moved.end(), [](const EdgeRec& x, const EdgeRec& y) { return x.key < y.key; });
-    // merge the two sorted runs, pooling equal keys (an edge can meet its twin in the other run or in its own)
-    merged.clear();
-    merged.reserve(E.size() + moved.size());
-    auto emit = [&](const EdgeRec& r) {
-      if (!merged.empty() && merged.back().key == r.key) {
-        EdgeRec& t = merged.back();
-        t.sum += r.sum;
-        t.count += r.count;
-        if (r.anchor < t.anchor) t.anchor = r.anchor;
-      } else {
-        merged.push_back(r);
+    // merge the renamed edges back, pooling equal keys: worker t owns one range of keys -- its share of the kept run and,
+    // from every worker's sorted renamed edges, the ones inside the range
+    size_t total_moved = 0;
+    for (int t = 0; t < T; ++t) total_moved += moved[(size_t)t].size();
+    parallel_for(T, [&](int t) {
+      const size_t klo = total_kept * (size_t)t / (size_t)T, khi = total_kept * (size_t)(t + 1) / (size_t)T;
+      // range of keys [first, last): boundaries are keys of the kept run (or everything when it is empty)
+      const uint64_t first = (t == 0 || total_kept == 0) ? 0 : kept_buf[klo].key;
+      const bool open_end = (t == T - 1) || total_kept == 0;
+      const uint64_t last = open_end ? 0 : kept_buf[khi].key;
+      if (total_kept == 0 && t != 0) { out[(size_t)t].clear(); return; }   // no splitters: worker 0 takes all renamed edges
+      std::vector<EdgeRec>& mv = mine[(size_t)t];
+      mv.clear();
+      auto by_key = [](const EdgeRec& x, uint64_t k) { return x.key < k; };
+      for (int s2 = 0; s2 < T; ++s2) {
+        const std::vector<EdgeRec>& src = moved[(size_t)s2];
+        auto b = std::lower_bound(src.begin(), src.end(), first, by_key);
+        auto e2 = open_end ? src.end() : std::lower_bound(src.begin(), src.end(), last, by_key);
+        mv.insert(mv.end(), b, e2);
       }
-    };
-    size_t i = 0, j = 0;
-    while (i < E.size() || j < moved.size()) {
-      if (j == moved.size() || (i < E.size() && E[i].key <= moved[j].key)) emit(E[i++]);
-      else emit(moved[j++]);
-    }
-    E.swap(merged);
-    (void)pruned;
+      std::sort(mv.begin(), mv.end(), [](const EdgeRec& x, const EdgeRec& y) { return x.key < y.key; });
+      std::vector<EdgeRec>& o = out[(size_t)t];
+      o.clear();
+      o.reserve((khi - klo) + mv.size());
+      auto emit = [&](const EdgeRec& r) {
+        if (!o.empty() && o.back().key == r.key) {
+          EdgeRec& q = o.back();
+          q.sum += r.sum;
+          q.count += r.count;
+          if (r.anchor < q.anchor) q.anchor = r.anchor;
+        } else {
+          o.push_back(r);
+        }
+      };
+      size_t i = klo, j = 0;
+      while (i < khi || j < mv.size()) {
+        if (j == mv.size() || (i < khi && kept_buf[i].key <= mv[j].key)) emit(kept_buf[i++]);
+        else emit(mv[j++]);
+      }
+    });
+    size_t total = 0;
+    for (int t = 0; t < T; ++t) { n_kept[(size_t)t] = total; total += out[(size_t)t].size(); }
+    E.resize(total);
+    parallel_for(T, [&](int t) { std::copy(out[(size_t)t].begin(), out[(size_t)t].end(), E.begin() + (std::ptrdiff_t)n_kept[(size_t)t]); });
+    (void)total_moved;
     // hand over to the sequential walk when a round costs more than the walk would for the same merges (the walk moves
     // every edge of a merged cluster through a hash table: a few microseconds per merge; the result does not depend on
     // where the hand-over happens)
@@ -395,6 +503,7 @@ int mutual_best_rounds(int64_t num_nodes, std::vector<EdgeRec>& E, double thr, s
 }  // namespace
 
 // CFB_AGGLOMERATE_MODE (development / tests): 0 = sequential walk only, 1 = rounds, then the walk (default), 2 = rounds until none merges, then the walk
+// CFB_AGGLOMERATE_THREADS: workers of the rounds (default: half the hardware threads, at most 16); the result does not depend on it
 extern "C" int cfb_agglomerate_edges_host(int64_t num_nodes, int64_t num_edges, const uint32_t* u, const uint32_t* v,
                                           const uint64_t* sum_fixed, const uint32_t* count, float threshold, uint32_t* root_of) {
   try {
@@ -418,7 +527,11 @@ extern "C" int cfb_agglomerate_edges_host(int64_t num_nodes, int64_t num_edges, 
       if (E[i].key == E[i - 1].key) throw std::invalid_argument("agglomerate: duplicate edge");
     std::vector<uint32_t> parent((size_t)num_nodes);
     for (int64_t i = 0; i < num_nodes; ++i) parent[i] = (uint32_t)i;
-    if (mode != 0) mutual_best_rounds(num_nodes, E, thr, parent, mode);
+    int threads = (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    if (const char* m = std::getenv("CFB_AGGLOMERATE_THREADS")) threads = std::max(1, std::min(64, std::atoi(m)));
+    size_t grain = 2048;
+    if (const char* m = std::getenv("CFB_AGGLOMERATE_GRAIN")) grain = (size_t)std::max(1, std::atoi(m));   // tests: many workers on tiny graphs
+    if (mode != 0) mutual_best_rounds(num_nodes, E, thr, parent, mode, threads, grain);
     // the walk on what is left: cluster labels are node ids of the contracted graph
     std::vector<uint32_t> root((size_t)num_nodes);
     for (int64_t i = 0; i < num_nodes; ++i) root[i] = (uint32_t)i;

@@ -156,10 +156,12 @@ def test_whole_operator_with_emulated_voxel_passes_and_the_native_merge_loop(emu
 # ------------------------------------------------------------------------------------------------------------
 # the host merge loop of the native library (no GPU involved)
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
-def test_native_merge_loop_against_the_oracle(monkeypatch, mode):
+@pytest.mark.parametrize("mode,threads,grain", [("0", "1", "2048"), ("1", "1", "2048"), ("1", "6", "500"), ("2", "3", "64")])
+def test_native_merge_loop_against_the_oracle(monkeypatch, mode, threads, grain):
     from chunkflow_b200 import _native
     monkeypatch.setenv("CFB_AGGLOMERATE_MODE", mode)
+    monkeypatch.setenv("CFB_AGGLOMERATE_THREADS", threads)
+    monkeypatch.setenv("CFB_AGGLOMERATE_GRAIN", grain)
     rng = np.random.default_rng(7)
     # (the last two graphs have more than 4096 edges: in mode 1 they go through rounds, pruning and the hand-over to the walk)
     for trial, (shape, thr, kind) in enumerate((((6, 10, 12), 0.5, 0), ((8, 12, 12), 0.3, 5), ((5, 9, 9), 0.8, 1), ((10, 16, 16), 0.45, 0),
@@ -192,14 +194,17 @@ def test_native_merge_loop_against_the_oracle(monkeypatch, mode):
         _native.agglomerate_edges_host(3, [1, 1], [2, 2], [1, 1], [1, 1], 0.5)   # duplicate edge
 
 
-@pytest.mark.parametrize("mode", ["0", "1", "2"])
-def test_native_merge_loop_fuzz_shapes_ties_and_odd_thresholds(monkeypatch, mode):
+@pytest.mark.parametrize("mode,threads,grain", [("0", "1", "2048"), ("1", "4", "2048"), ("2", "1", "2048"), ("2", "5", "3"), ("2", "8", "1")])
+def test_native_merge_loop_fuzz_shapes_ties_and_odd_thresholds(monkeypatch, mode, threads, grain):
     """Random, chain, star + ring and dense graphs with few distinct means (ties everywhere), means above 1 (negative scores),
     thresholds 0 / 1 / 2 / negative / inf: the native loop == the oracle's heap walk, in each of its modes -- 0: the sequential
     walk alone (bucket queue, shorter list moved), 2: rounds of mutual-best merges until none is left (on graphs of any size:
-    the reducibility argument put to the test, ties included), 1: the product's mix (rounds on large graphs, then the walk)."""
+    the reducibility argument put to the test, ties included), 1: the product's mix (rounds on large graphs, then the walk);
+    the rounds with one worker and with several workers on slices of a few edges each (atomic minima, range-partitioned merge)."""
     from chunkflow_b200 import _native
     monkeypatch.setenv("CFB_AGGLOMERATE_MODE", mode)
+    monkeypatch.setenv("CFB_AGGLOMERATE_THREADS", threads)
+    monkeypatch.setenv("CFB_AGGLOMERATE_GRAIN", grain)
     rng = np.random.default_rng(123)
     for t in range(160):
         n = int(rng.integers(2, 40))

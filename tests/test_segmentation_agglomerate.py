@@ -232,6 +232,27 @@ def test_native_merge_loop_fuzz_shapes_ties_and_odd_thresholds(monkeypatch, mode
             assert np.array_equal(_native.agglomerate_edges_host(n, u, v, s, c, thr), A.agglomerate_edges(n, u, v, s, c, thr)), (t, thr)
 
 
+def test_threaded_rounds_under_thread_sanitizer(tmp_path):
+    """The worker threads of the rounds share arrays through relaxed atomics and disjoint slices: ThreadSanitizer must stay
+    silent, and eight workers must return what one worker returns."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "tsan_agglomerate"
+    cmd = [gxx, "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-x", "c++", "-I/usr/local/cuda/include",
+           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "chunkflow_b200", "csrc"),
+           os.path.join(ROOT, "chunkflow_b200", "csrc", "agglomerate_host.cu"),
+           os.path.join(ROOT, "tests", "host_emulation", "tsan_agglomerate.cpp"), "-o", str(exe), "-lpthread"]
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("no ThreadSanitizer build here: " + build.stderr[-300:])
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    if "unexpected memory mapping" in run.stderr or "FATAL: ThreadSanitizer" in run.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this sandbox")
+    assert run.returncode == 0 and "bad 0" in run.stdout, run.stdout[-500:] + run.stderr[-2000:]
+    assert "WARNING: ThreadSanitizer" not in run.stderr, run.stderr[-3000:]
+
+
 def test_plugin_refuses_other_scoring_functions_and_needs_a_gpu():
     from chunkflow_b200 import Chunk
     from chunkflow_b200.plugins import agglomerate

@@ -140,3 +140,26 @@ def test_identity_random_geometries_oracle_equals_reference(ref):
         assert np.array_equal(np.asarray(r.array), o), (ps, ov, size)
         assert tuple(r.voxel_offset) == tuple(o_off)
         done += 1
+
+
+def test_cropped_output_random_aligned_geometries(ref):
+    """Row f2 on random configurations: output patch smaller than the input patch (crop margin per patch), aligned chunk
+    built from `patch_num`, no chunk-wise mask, random voxel offset: oracle == real reference, bit for bit."""
+    rng = np.random.default_rng(31)
+    for _ in range(8):
+        crop = tuple(int(v) for v in rng.integers(0, 4, 3))
+        out_ps = tuple(int(v) for v in rng.integers(4, 11, 3))
+        in_ps = tuple(o + 2 * c for o, c in zip(out_ps, crop))
+        ov = tuple(int(rng.integers(1, o // 2 + 1)) for o in out_ps)
+        num = tuple(int(v) for v in rng.integers(1, 4, 3))
+        in_ov = tuple(2 * c + o for c, o in zip(crop, ov))
+        size = tuple((p - io) * n + io for p, io, n in zip(in_ps, in_ov, num))       # reference inferencer.py:131-135
+        img = rng.integers(1, 256, size=size, dtype=np.uint8)
+        off = tuple(int(v) for v in rng.integers(-50, 50, 3))
+        kw = dict(input_patch_size=in_ps, output_patch_size=out_ps, output_patch_overlap=ov)
+        c = int(rng.integers(1, 3))
+        r = _run_ref(ref, img, offset=off, num_output_channels=c, framework="identity", batch_size=int(rng.integers(1, 4)),
+                     mask_output_chunk=False, patch_num=num, **kw)
+        o, o_off = O.infer_chunk(img, off, num_output_channels=c, framework="identity", mask_output_chunk=False, **kw)
+        assert tuple(r.voxel_offset) == o_off and r.shape == o.shape, (in_ps, out_ps, ov, num)
+        assert np.array_equal(np.asarray(r.array), o), (in_ps, out_ps, ov, num)

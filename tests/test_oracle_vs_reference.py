@@ -163,3 +163,23 @@ def test_cropped_output_random_aligned_geometries(ref):
         o, o_off = O.infer_chunk(img, off, num_output_channels=c, framework="identity", mask_output_chunk=False, **kw)
         assert tuple(r.voxel_offset) == o_off and r.shape == o.shape, (in_ps, out_ps, ov, num)
         assert np.array_equal(np.asarray(r.array), o), (in_ps, out_ps, ov, num)
+
+
+def test_myelin_threshold_and_float_input_random(ref):
+    """`--mask-myelin-threshold` (inferencer.py:468-477 -> Chunk.mask_using_last_channel, chunk/base.py:685-689) and a float32
+    input chunk (no /255), identity backend with 4 output channels, random geometry: oracle == real reference, bit for bit."""
+    rng = np.random.default_rng(41)
+    for k in range(6):
+        ps = tuple(int(v) for v in rng.integers(4, 11, 3))
+        ov = tuple(int(rng.integers(1, p // 2 + 1)) for p in ps)
+        size = tuple(int(p + rng.integers(0, 2 * p)) for p in ps)
+        if k % 2:
+            img = rng.random(size, dtype=np.float32)
+        else:
+            img = rng.integers(1, 255, size=size, dtype=np.uint8)
+        thr = float(rng.uniform(0.2, 0.8))
+        kw = dict(input_patch_size=ps, output_patch_overlap=ov, num_output_channels=4, mask_myelin_threshold=thr)
+        r = _run_ref(ref, img, framework="identity", mask_output_chunk=True, batch_size=2, **kw)
+        o, _ = O.infer_chunk(img, framework="identity", **kw)
+        assert r.shape == o.shape == (3,) + size
+        assert np.array_equal(np.asarray(r.array), o), (ps, ov, size, k)

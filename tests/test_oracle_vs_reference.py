@@ -183,3 +183,23 @@ def test_myelin_threshold_and_float_input_random(ref):
         o, _ = O.infer_chunk(img, framework="identity", **kw)
         assert r.shape == o.shape == (3,) + size
         assert np.array_equal(np.asarray(r.array), o), (ps, ov, size, k)
+
+
+def test_chunk_create_sin_and_zero_match_the_reference(ref):
+    """`create-chunk` inputs (chunk/base.py:139-199): pattern 'sin' / 'zero', uint8 and float32, 3-D and 4-D sizes: the product's
+    Chunk.create == the real reference's, bit for bit (row a17; 'random' deviates by design: the reference relabels with cc3d)."""
+    from chunkflow_b200 import Chunk as OurChunk
+    _, RefChunk, _ = ref
+    rng = np.random.default_rng(5)
+    for k in range(10):
+        size = tuple(int(v) for v in rng.integers(1, 40, 3))
+        if k % 3 == 2:
+            size = (int(rng.integers(1, 4)),) + size
+        for dtype in ("uint8", "float32"):
+            for pattern in ("sin", "zero"):
+                off = tuple(int(v) for v in rng.integers(-9, 9, 3))
+                with redirect_stdout(io.StringIO()):
+                    want = RefChunk.create(size=size, dtype=np.dtype(dtype), pattern=pattern, voxel_offset=off, voxel_size=(4, 4, 40))
+                got = OurChunk.create(size=size, dtype=np.dtype(dtype), pattern=pattern, voxel_offset=off, voxel_size=(4, 4, 40))
+                assert got.array.dtype == want.array.dtype and np.array_equal(got.array, np.asarray(want.array)), (size, dtype, pattern)
+                assert tuple(got.voxel_offset) == tuple(want.voxel_offset) and tuple(got.voxel_size) == tuple(want.voxel_size)

@@ -203,3 +203,39 @@ def test_chunk_create_sin_and_zero_match_the_reference(ref):
                 got = OurChunk.create(size=size, dtype=np.dtype(dtype), pattern=pattern, voxel_offset=off, voxel_size=(4, 4, 40))
                 assert got.array.dtype == want.array.dtype and np.array_equal(got.array, np.asarray(want.array)), (size, dtype, pattern)
                 assert tuple(got.voxel_offset) == tuple(want.voxel_offset) and tuple(got.voxel_size) == tuple(want.voxel_size)
+
+
+def test_chunk_glue_cutout_blend_crop_match_the_reference(ref):
+    """Row a16: the product's host `Chunk` (cutout in global slices, blend with clipping at the buffer border, crop_margin,
+    mask_using_last_channel) against the real reference's `Chunk` on random boxes (chunk/base.py:685-726,761-807)."""
+    from chunkflow_b200 import Chunk as OurChunk
+    _, RefChunk, _ = ref
+    rng = np.random.default_rng(17)
+    for _ in range(25):
+        c = int(rng.integers(1, 4))
+        size = tuple(int(v) for v in rng.integers(6, 20, 3))
+        off = tuple(int(v) for v in rng.integers(-20, 20, 3))
+        base = rng.random((c,) + size, dtype=np.float32)
+        ours, theirs = OurChunk(base.copy(), voxel_offset=off), RefChunk(base.copy(), voxel_offset=off)
+        # cutout of a random inner box, global coordinates
+        lo = tuple(int(rng.integers(0, s - 2)) for s in size)
+        hi = tuple(int(rng.integers(l + 1, s + 1)) for l, s in zip(lo, size))
+        sl = tuple(slice(o + l, o + h) for o, l, h in zip(off, lo, hi))
+        a, b = ours.cutout(sl), theirs.cutout(sl)
+        assert np.array_equal(a.array, np.asarray(b.array)) and tuple(a.voxel_offset) == tuple(b.voxel_offset)
+        # blend a patch that sticks out of the buffer on some sides
+        psz = tuple(int(v) for v in rng.integers(3, 10, 3))
+        poff = tuple(int(o + rng.integers(-p + 1, s)) for o, p, s in zip(off, psz, size))
+        patch = rng.random((c,) + psz, dtype=np.float32)
+        ours.blend(OurChunk(patch.copy(), voxel_offset=poff))
+        theirs.blend(RefChunk(patch.copy(), voxel_offset=poff))
+        assert np.array_equal(ours.array, np.asarray(theirs.array))
+        # crop_margin, mask_using_last_channel
+        m = tuple(int(rng.integers(0, (s - 1) // 2)) for s in size)
+        a, b = ours.crop_margin(m), theirs.crop_margin(m)
+        assert np.array_equal(a.array, np.asarray(b.array)) and tuple(a.voxel_offset) == tuple(b.voxel_offset)
+        if c > 1:
+            thr = float(rng.uniform(0.2, 0.8))
+            a = OurChunk(base.copy(), voxel_offset=off).mask_using_last_channel(thr)
+            b = RefChunk(base.copy(), voxel_offset=off).mask_using_last_channel(threshold=thr)
+            assert np.array_equal(a.array, np.asarray(b.array)) and tuple(a.voxel_offset) == tuple(b.voxel_offset)

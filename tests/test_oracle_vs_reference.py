@@ -239,3 +239,23 @@ def test_chunk_glue_cutout_blend_crop_match_the_reference(ref):
             a = OurChunk(base.copy(), voxel_offset=off).mask_using_last_channel(thr)
             b = RefChunk(base.copy(), voxel_offset=off).mask_using_last_channel(threshold=thr)
             assert np.array_equal(a.array, np.asarray(b.array)) and tuple(a.voxel_offset) == tuple(b.voxel_offset)
+
+
+def test_transform_sequences_literal_mode_matches_the_reference(ref):
+    """Row a15, host plug-in path: the product's TransformSequences('reference') == the real reference's
+    (flow/divid_conquer/transform.py:114-156) on random 5-D buffers -- every one of the 8 forward copies and 8 backward results."""
+    from chunkflow.flow.divid_conquer.transform import TransformSequences as RefTS
+    from chunkflow_b200.flow.divid_conquer.transform import TransformSequences
+    ours, theirs = TransformSequences('reference'), RefTS()
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        b, c, z, n = (int(v) for v in (rng.integers(1, 4), rng.integers(1, 4), rng.integers(1, 5), rng.integers(2, 9)))
+        x = rng.random((b, c, z, n, n), dtype=np.float32)
+        fo, ft = ours.forward(x), theirs.forward(x)
+        assert len(fo) == len(ft) == 8
+        for p, q in zip(fo, ft):
+            assert np.array_equal(p, np.asarray(q))
+        outs = [rng.random(p.shape, dtype=np.float32) for p in fo]
+        bo, bt = ours.backward([o.copy() for o in outs]), theirs.backward([o.copy() for o in outs])
+        for p, q in zip(bo, bt):
+            assert np.array_equal(p, np.asarray(q))

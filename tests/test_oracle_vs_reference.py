@@ -259,3 +259,30 @@ def test_transform_sequences_literal_mode_matches_the_reference(ref):
         bo, bt = ours.backward([o.copy() for o in outs]), theirs.backward([o.copy() for o in outs])
         for p, q in zip(bo, bt):
             assert np.array_equal(p, np.asarray(q))
+
+
+def test_plugin_surface_matches_the_reference(ref):
+    """Rows a8 / a10 / B3: the plugin base class carries the attributes the reference's Inferencer reads, with the same values,
+    and `Universal` drives the REFERENCE'S OWN example plugin file (examples/inference/universal_identity.py) to the same
+    per-patch result as the reference's Universal."""
+    import os
+    from chunkflow.flow.divid_conquer.patch.universal import Universal as RefUniversal
+    from chunkflow_b200.flow.divid_conquer.patch.universal import Universal
+    plugin = os.path.join(H.REFERENCE_ROOT, "examples", "inference", "universal_identity.py")
+    rng = np.random.default_rng(23)
+    for _ in range(5):
+        out_ps = tuple(int(v) for v in rng.integers(4, 12, 3))
+        crop = tuple(int(v) for v in rng.integers(0, 3, 3))
+        in_ps = tuple(o + 2 * c for o, c in zip(out_ps, crop))
+        ov = tuple(int(rng.integers(1, o // 2 + 1)) for o in out_ps)
+        kw = dict(input_patch_size=in_ps, output_patch_size=out_ps, output_patch_overlap=ov, num_output_channels=1)
+        ours, theirs = Universal(plugin, None, **kw), RefUniversal(plugin, None, **kw)
+        for name in ("input_patch_size", "output_patch_size", "output_patch_overlap", "num_output_channels", "crop_margin",
+                     "input_patch_overlap", "input_patch_stride", "output_patch_stride"):
+            assert tuple(np.atleast_1d(getattr(ours, name))) == tuple(np.atleast_1d(getattr(theirs, name))), name
+        assert np.array_equal(np.asarray(ours.output_patch_mask_numpy), np.asarray(theirs.output_patch_mask_numpy))
+        # the example plugin multiplies by the OUTPUT patch mask: feed it a patch of the output size, like its own test does
+        patch = rng.random((2, 1) + out_ps, dtype=np.float32)
+        assert np.array_equal(ours(patch.copy()), theirs(patch.copy()))
+        big = rng.random((1, 3) + in_ps, dtype=np.float32)
+        assert np.array_equal(ours._crop_output_patch(big), theirs._crop_output_patch(big))

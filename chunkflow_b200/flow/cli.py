@@ -61,7 +61,8 @@ def operator(func):
 @main.command("create-chunk")
 @click.option("--name", type=str, default="create-chunk", help="name of operator")
 @click.option("--size", "-s", type=click.INT, nargs=3, default=(64, 64, 64), help="the size of created chunk")
-@click.option("--dtype", type=click.Choice(["uint8", "float32"]), default="uint8", help="the data type of chunk")
+@click.option("--dtype", "-d", type=click.Choice(["uint8", "float32", "float64"]), default="uint8",
+              help="the data type of chunk (the reference's integer label types need cc3d and are not part of this path)")
 @click.option("--pattern", "-p", type=click.Choice(["sin", "random", "zero"]), default="sin")
 @click.option("--voxel-offset", "-t", type=click.INT, nargs=3, default=(0, 0, 0), help="offset in voxel number.")
 @click.option("--voxel-size", "-e", type=click.INT, nargs=3, default=(1, 1, 1), help="voxel size in nm")

@@ -286,3 +286,64 @@ def test_plugin_surface_matches_the_reference(ref):
         assert np.array_equal(ours(patch.copy()), theirs(patch.copy()))
         big = rng.random((1, 3) + in_ps, dtype=np.float32)
         assert np.array_equal(ours._crop_output_patch(big), theirs._crop_output_patch(big))
+
+
+def test_cli_inference_options_match_the_reference_source():
+    """Boundary B1: every option of the reference's `inference` command (flow/flow.py:1850-1893, read as text: importing that
+    module needs cloud packages) exists here with the same flags, the same default and the same `required` -- plus the extra
+    `b200` framework choice.  Also `create-chunk`'s and `connected-components`' flag names."""
+    import ast
+    import os
+    import re
+    from chunkflow_b200.flow import cli
+    src = open(os.path.join(H.REFERENCE_ROOT, "chunkflow", "flow", "flow.py")).read()
+
+    def reference_options(command):
+        seg = src[src.index(f"@main.command('{command}')"):]
+        seg = seg[:seg.index("\ndef ")]
+        opts = []
+        for m in re.finditer(r"@click\.option\((.*?)\)\s*(?=@click\.option|@operator|@generator|@main|$)", seg, re.S):
+            body = m.group(1)
+            flags = re.findall(r"'(-{1,2}[A-Za-z][\w/-]*)'", body.split("help=")[0])
+            default = re.search(r"default=(\([^)]*\)|[^,\s)]+)", body)
+            try:
+                value = ast.literal_eval(default.group(1)) if default else None
+            except (ValueError, SyntaxError):
+                value = None     # (an expression such as Cartesian(...): only compared for `inference`, whose defaults are literals)
+            opts.append((flags, value, "required=True" in body))
+        return opts
+
+    def ours(command):
+        table = {}
+        for p in command.params:
+            for o in p.opts + p.secondary_opts:
+                table[o] = p
+        return table
+
+    mine = ours(cli.inference)
+    ref_opts = reference_options("inference")
+    assert len(ref_opts) == 19
+    for flags, default, required in ref_opts:
+        for f in flags:
+            for part in f.split("/"):
+                assert part in mine, part
+        p = mine[flags[0].split("/")[0]]
+        got = p.default
+        if isinstance(default, tuple):
+            got = tuple(got)
+        assert got == default or (default is None and got in (None, ())), (flags, default, p.default)
+        assert bool(p.required) == required, flags
+    assert set(mine["--framework"].type.choices) == {"universal", "identity", "pytorch", "b200"}
+    for command, obj in (("create-chunk", cli.create_chunk), ("connected-components", cli.connected_components),
+                         ("normalize-contrast", cli.normalize_contrast), ("crop-margin", cli.crop_margin), ("quantize", cli.quantize)):
+        have = ours(obj)
+        for flags, _, _ in reference_options(command):
+            for f in flags:
+                if f == "--crop-bbox/--no-crop-bbox":   # crop-margin's bounding-box bookkeeping belongs to the storage operators
+                    continue
+                for part in f.split("/"):
+                    assert part in have, (command, part)
+
+
+test_cli_inference_options_match_the_reference_source = pytest.mark.skipif(not H.available(), reason="no reference tree")(
+    test_cli_inference_options_match_the_reference_source)

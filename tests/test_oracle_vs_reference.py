@@ -347,3 +347,19 @@ def test_cli_inference_options_match_the_reference_source():
 
 test_cli_inference_options_match_the_reference_source = pytest.mark.skipif(not H.available(), reason="no reference tree")(
     test_cli_inference_options_match_the_reference_source)
+
+
+def test_inferencer_constructor_signature_matches_the_reference(ref):
+    """Boundary B2: the constructor keywords of the reference's Inferencer (inferencer.py:36-54), in order, with the same
+    defaults; the product appends `device` and `precision`."""
+    import inspect
+    from chunkflow_b200 import Inferencer as Ours
+    RefInferencer, _, _ = ref
+    theirs = [(n, p.default) for n, p in inspect.signature(RefInferencer.__init__).parameters.items()]
+    mine = [(n, p.default) for n, p in inspect.signature(Ours.__init__).parameters.items()]
+    assert [n for n, _ in mine[:len(theirs)]] == [n for n, _ in theirs]
+    for (n, d_mine), (_, d_ref) in zip(mine, theirs):
+        assert d_mine == d_ref or (d_mine is inspect.Parameter.empty and d_ref is inspect.Parameter.empty), (n, d_mine, d_ref)
+    assert [n for n, _ in mine[len(theirs):]] == ["device", "precision"]
+    for name in ("compute_device", "__enter__", "__exit__", "__call__"):
+        assert hasattr(Ours, name) and hasattr(RefInferencer, name)
